@@ -1,0 +1,529 @@
+// C ABI of libagdiff_b200.so (see include/agdiff_b200.h): handle/weights/batch management, the
+// forward pass, and the sampling loop replayed from two captured CUDA graphs (local-only step and
+// local+global step).  No CPU fallback: every entry point needs a CUDA device.
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace agd {
+void set_encoder_attributes();
+void set_schnet_attributes();
+void set_gin_attributes();
+}  // namespace agd
+
+using namespace agd;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(AGD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+  } while (0)
+
+struct Slot {
+  std::string name;
+  int64_t size;
+  const float** field;
+};
+
+struct agd_handle {
+  agd_config cfg;
+  ModelW w;
+  std::vector<Slot> slots;
+  float* dev_weights = nullptr;
+  int64_t n_weights = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  int64_t launches = 0;
+};
+
+struct agd_batch {
+  agd_handle* h;
+  BatchDev d;
+  void* slab = nullptr;
+  int64_t slab_bytes = 0;
+};
+
+static void build_slots(agd_handle* h) {
+  auto& s = h->slots;
+  ModelW& w = h->w;
+  auto add = [&](const std::string& n, int64_t sz, const float** f) { s.push_back({n, sz, f}); };
+  const int H = HID;
+  add("enc.fe_w", H, &w.enc.fe_w);
+  add("enc.fe_b", H, &w.enc.fe_b);
+  add("enc.T1", 100 * H, &w.enc.T1);
+  add("enc.W1", H * H, &w.enc.W1);
+  add("enc.T2", 100 * H, &w.enc.T2);
+  add("enc.M2", H * H, &w.enc.M2);
+  add("enc.C2", H * H, &w.enc.C2);
+  add("enc.c2b", H, &w.enc.c2b);
+  add("sch.emb", 100 * H, &w.sch_emb);
+  for (int k = 0; k < h->cfg.num_convs; ++k) {
+    BlkW& b = w.blk[k];
+    const std::string p = "blk" + std::to_string(k) + ".";
+    add(p + "L1a", H * 128, &b.L1a);   add(p + "l1ab", 128, &b.l1ab);
+    add(p + "L1b", H * 64, &b.L1b);    add(p + "l1bb", 64, &b.l1bb);
+    add(p + "F1a", H * 128, &b.F1a);   add(p + "f1ab", 128, &b.f1ab);
+    add(p + "F2a", 128 * 128, &b.F2a); add(p + "f2ab", 128, &b.f2ab);
+    add(p + "F1b", H * 64, &b.F1b);    add(p + "f1bb", 64, &b.f1bb);
+    add(p + "F2b", 64 * 64, &b.F2b);   add(p + "f2bb", 64, &b.f2bb);
+    add(p + "dw1", 128, &b.dw1);       add(p + "dw2", 128, &b.dw2);
+    add(p + "L2a", 128 * H, &b.L2a);   add(p + "l2ab", H, &b.l2ab);
+    add(p + "L2b", 64 * H, &b.L2b);    add(p + "l2bb", H, &b.l2bb);
+    add(p + "LIN", 256 * H, &b.LIN);   add(p + "linb", H, &b.linb);
+    add(p + "A1", H * 64, &b.A1);      add(p + "a1b", 64, &b.a1b);
+    add(p + "a2w", 64, &b.a2w);
+    add(p + "S1", H * 8, &b.S1);       add(p + "S2", 8 * H, &b.S2);
+    add(p + "sc", 4, &b.sc);
+  }
+  auto add_pair = [&](const std::string& p, PairW& q) {
+    add(p + "P1h", H * H, &q.P1h); add(p + "P1e", H * H, &q.P1e); add(p + "p1b", H, &q.p1b);
+    add(p + "P2", H * 64, &q.P2);  add(p + "p2b", 64, &q.p2b);
+    add(p + "p3w", 64, &q.p3w);    add(p + "p3b", 1, &q.p3b);
+  };
+  add_pair("pg.", w.pg);
+  add_pair("pl.", w.pl);
+  add("gin.emb", 100 * H, &w.gin_emb);
+  for (int k = 0; k < h->cfg.num_convs_local; ++k) {
+    GinW& g = w.gin[k];
+    const std::string p = "gin" + std::to_string(k) + ".";
+    add(p + "G1", H * H, &g.G1); add(p + "g1b", H, &g.g1b);
+    add(p + "G2", H * H, &g.G2); add(p + "g2b", H, &g.g2b);
+    add(p + "sc", 1, &g.sc);
+  }
+}
+
+static LaunchCtx make_ctx(agd_handle* h) {
+  LaunchCtx c;
+  c.stream = h->stream;
+  c.num_sms = h->num_sms;
+  c.launch_counter = &h->launches;
+  c.cutoff = h->cfg.cutoff;
+  c.smooth = h->cfg.smooth_conv;
+  c.num_convs = h->cfg.num_convs;
+  c.num_convs_local = h->cfg.num_convs_local;
+  return c;
+}
+
+// order library work after everything already queued on the caller's stream, and back
+static int enter(agd_handle* h, void* user_stream) {
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaEventRecord(h->ev_in, (cudaStream_t)user_stream));
+  CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in, 0));
+  return AGD_OK;
+}
+static int leave(agd_handle* h, void* user_stream) {
+  CUDA_TRY(cudaEventRecord(h->ev_out, h->stream));
+  CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)user_stream, h->ev_out, 0));
+  CUDA_TRY(cudaGetLastError());
+  return AGD_OK;
+}
+
+// ------------------------------------------------------------------ launch sequences
+static void run_local_branch(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos, const float** h_out) {
+  launch_encoder_local(c, b, w, pos);
+  launch_gin_embed(c, b, w);
+  const float* x_in = b.gx0;
+  float* x_out = b.gx1;
+  for (int k = 0; k < c.num_convs_local; ++k) {
+    launch_gin_layer(c, b, w, k, x_in, x_out);
+    const float* t = x_in;
+    x_in = x_out;
+    x_out = const_cast<float*>(t);
+  }
+  launch_pair_local(c, b, w, x_in);
+  if (h_out) *h_out = x_in;
+}
+
+static void run_global_branch(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos) {
+  launch_build_edges(c, b, pos);
+  launch_encoder_global(c, b, w);
+  launch_schnet_node(c, b, w, -1);
+  for (int k = 0; k < c.num_convs; ++k) {
+    launch_filters(c, b, w, k);
+    launch_aggregate(c, b.xcat, b.filt, b.e_src, b.in_ptr, b.n_atoms, 192, b.agg);
+    launch_schnet_node(c, b, w, k);
+  }
+  launch_pair_global(c, b, w);
+}
+
+extern "C" {
+
+int agd_abi_version(void) { return AGD_ABI_VERSION; }
+const char* agd_last_error(void) { return g_err.c_str(); }
+
+int agd_create(const agd_config* cfg, agd_handle** out) {
+  if (!cfg || !out) return fail(AGD_ERR_INVALID, "null argument");
+  if (cfg->hidden_dim != HID) return fail(AGD_ERR_INVALID, "hidden_dim must be 128 (schnet.py:190-192 pins Linear(256, hidden))");
+  if (cfg->num_convs < 1 || cfg->num_convs > MAX_BLOCKS) return fail(AGD_ERR_INVALID, "num_convs out of range");
+  if (cfg->num_convs_local < 1 || cfg->num_convs_local > MAX_GIN) return fail(AGD_ERR_INVALID, "num_convs_local out of range");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(AGD_ERR_CUDA, "no such CUDA device");
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  agd_handle* h = new agd_handle();
+  h->cfg = *cfg;
+  std::memset(&h->w, 0, sizeof(h->w));
+  build_slots(h);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  h->num_sms = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+  set_encoder_attributes();
+  set_schnet_attributes();
+  set_gin_attributes();
+  CUDA_TRY(cudaGetLastError());
+  *out = h;
+  return AGD_OK;
+}
+
+void agd_destroy(agd_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->dev_weights) cudaFree(h->dev_weights);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
+  delete h;
+}
+
+int agd_weight_slot_count(const agd_handle* h) { return h ? (int)h->slots.size() : 0; }
+const char* agd_weight_slot_name(const agd_handle* h, int slot) {
+  if (!h || slot < 0 || slot >= (int)h->slots.size()) return nullptr;
+  return h->slots[slot].name.c_str();
+}
+int64_t agd_weight_slot_size(const agd_handle* h, int slot) {
+  if (!h || slot < 0 || slot >= (int)h->slots.size()) return -1;
+  return h->slots[slot].size;
+}
+
+int agd_load_weights(agd_handle* h, const float* packed_host, const int64_t* slot_offsets, int n_slots, int64_t n_floats) {
+  if (!h || !packed_host || !slot_offsets) return fail(AGD_ERR_INVALID, "null argument");
+  if (n_slots != (int)h->slots.size()) return fail(AGD_ERR_INVALID, "slot count mismatch");
+  for (int i = 0; i < n_slots; ++i) {
+    if (slot_offsets[i] < 0 || slot_offsets[i] + h->slots[i].size > n_floats || (slot_offsets[i] % 4) != 0)
+      return fail(AGD_ERR_INVALID, "bad offset for slot " + h->slots[i].name);
+  }
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->n_weights != n_floats) {
+    if (h->dev_weights) CUDA_TRY(cudaFree(h->dev_weights));
+    h->dev_weights = nullptr;
+    CUDA_TRY(cudaMalloc(&h->dev_weights, sizeof(float) * (size_t)n_floats));
+    h->n_weights = n_floats;
+  }
+  CUDA_TRY(cudaMemcpy(h->dev_weights, packed_host, sizeof(float) * (size_t)n_floats, cudaMemcpyHostToDevice));
+  for (int i = 0; i < n_slots; ++i) *h->slots[i].field = h->dev_weights + slot_offsets[i];
+  return AGD_OK;
+}
+
+}  // extern "C"
+
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  template <class T>
+  T* take(size_t n) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off = align_up(off + n * sizeof(T));
+    return p;
+  }
+};
+
+static void carve(BatchDev& d, Carver& c) {
+  const size_t N = (size_t)d.n_atoms, E = (size_t)(d.cap > 0 ? d.cap : 1), L = (size_t)(d.n_local > 0 ? d.n_local : 1);
+  d.adj = c.take<unsigned>(N * MAXW);
+  d.adjT = c.take<unsigned>(N * MAXW);
+  d.in_deg = c.take<int>(N);
+  d.out_deg = c.take<int>(N);
+  d.in_ptr = c.take<int>(N + 1);
+  d.out_ptr = c.take<int>(N + 1);
+  d.counters = c.take<int>(8);
+  d.e_src = c.take<int>(E);
+  d.e_dst = c.take<int>(E);
+  d.e_type = c.take<int>(E);
+  d.e_canon = c.take<int>(E);
+  d.e_len = c.take<float>(E);
+  d.c_src = c.take<int>(E);
+  d.c_dst = c.take<int>(E);
+  d.c_type = c.take<int>(E);
+  d.c_len = c.take<float>(E);
+  d.s_csc = c.take<float>(E);
+  d.s_canon = c.take<float>(E);
+  d.lc_len = c.take<float>(L);
+  d.lcc_len = c.take<float>(L);
+  d.sl_csc = c.take<float>(L);
+  d.sl_canon = c.take<float>(L);
+  d.ea_loc = c.take<float>(L * HID);
+  d.g2 = c.take<float>(E * HID);
+  d.filt = c.take<float>(E * 192);
+  d.h = c.take<float>(N * HID);
+  d.xcat = c.take<float>(N * 192);
+  d.agg = c.take<float>(N * 192);
+  d.gx0 = c.take<float>(N * HID);
+  d.gx1 = c.take<float>(N * HID);
+}
+
+static int check_desc(const agd_batch_desc* d) {
+  if (!d) return fail(AGD_ERR_INVALID, "null batch descriptor");
+  if (d->n_atoms <= 0 || d->n_mols <= 0) return fail(AGD_ERR_INVALID, "empty batch");
+  if (d->edge_capacity < 0 || d->edge_capacity > (int64_t)INT_MAX - TM) return fail(AGD_ERR_CAPACITY, "edge capacity exceeds int32 indexing; split the batch");
+  if (!d->atom_type || !d->mol_ptr || !d->atom_mol || !d->mol_gid || !d->st_in_ptr || !d->lc_in_ptr || !d->lc_out_ptr)
+    return fail(AGD_ERR_INVALID, "missing topology pointer");
+  return AGD_OK;
+}
+
+extern "C" {
+
+int64_t agd_batch_workspace_bytes(const agd_handle* h, const agd_batch_desc* d) {
+  (void)h;
+  if (check_desc(d) != AGD_OK) return -1;
+  BatchDev t{};
+  t.n_atoms = d->n_atoms;
+  t.cap = d->edge_capacity;
+  t.n_local = d->n_local;
+  Carver c{nullptr};
+  carve(t, c);
+  return (int64_t)c.off;
+}
+
+int agd_batch_create(agd_handle* h, const agd_batch_desc* d, agd_batch** out) {
+  if (!h || !out) return fail(AGD_ERR_INVALID, "null argument");
+  int rc = check_desc(d);
+  if (rc != AGD_OK) return rc;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  agd_batch* b = new agd_batch();
+  b->h = h;
+  BatchDev& v = b->d;
+  std::memset(&v, 0, sizeof(v));
+  v.n_atoms = d->n_atoms; v.n_mols = d->n_mols; v.n_static = d->n_static; v.n_local = d->n_local; v.cap = d->edge_capacity;
+  v.atom_type = d->atom_type; v.mol_ptr = d->mol_ptr; v.atom_mol = d->atom_mol; v.mol_gid = d->mol_gid;
+  v.st_src = d->st_src; v.st_dst = d->st_dst; v.st_type = d->st_type; v.st_in_ptr = d->st_in_ptr;
+  v.lc_src = d->lc_src; v.lc_dst = d->lc_dst; v.lc_type = d->lc_type; v.lc_in_ptr = d->lc_in_ptr;
+  v.lc_canon = d->lc_canon; v.lc_out_ptr = d->lc_out_ptr; v.lc_cdst = d->lc_cdst;
+  Carver sz{nullptr};
+  carve(v, sz);
+  b->slab_bytes = (int64_t)sz.off;
+  cudaError_t e = cudaMalloc(&b->slab, sz.off);
+  if (e != cudaSuccess) {
+    delete b;
+    return fail(AGD_ERR_CUDA, std::string("workspace cudaMalloc(") + std::to_string(sz.off) + "): " + cudaGetErrorString(e));
+  }
+  Carver cv{reinterpret_cast<char*>(b->slab)};
+  carve(v, cv);
+  e = cudaMemset(v.counters, 0, 8 * sizeof(int));
+  if (e != cudaSuccess) {
+    cudaFree(b->slab);
+    delete b;
+    return fail(AGD_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
+  }
+  *out = b;
+  return AGD_OK;
+}
+
+void agd_batch_destroy(agd_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->h->cfg.device);
+  cudaStreamSynchronize(b->h->stream);
+  if (b->d.sched) cudaFree(b->d.sched);
+  if (b->slab) cudaFree(b->slab);
+  delete b;
+}
+
+static int check_ready(agd_handle* h, agd_batch* b) {
+  if (!h || !b) return fail(AGD_ERR_INVALID, "null handle/batch");
+  if (!h->dev_weights) return fail(AGD_ERR_INVALID, "weights not loaded (agd_load_weights)");
+  return AGD_OK;
+}
+
+static int check_overflow(agd_batch* b) {
+  int flag[4];
+  CUDA_TRY(cudaMemcpy(flag, b->d.counters, sizeof(flag), cudaMemcpyDeviceToHost));
+  if (flag[3] != 0) return fail(AGD_ERR_CAPACITY, "a molecule exceeds AGD_MAX_MOL_ATOMS (256)");
+  if ((int64_t)flag[0] > b->d.cap) return fail(AGD_ERR_CAPACITY, "edge count exceeded the declared capacity");
+  return AGD_OK;
+}
+
+int agd_build_edges(agd_handle* h, agd_batch* b, const float* pos, const agd_forward_out* out, void* stream) {
+  int rc = check_ready(h, b);
+  if (rc) return rc;
+  if (!pos || !out) return fail(AGD_ERR_INVALID, "null argument");
+  if ((rc = enter(h, stream))) return rc;
+  LaunchCtx c = make_ctx(h);
+  launch_build_edges(c, b->d, pos);
+  launch_export_edges(c, b->d, *out, false);
+  return leave(h, stream);
+}
+
+int agd_forward(agd_handle* h, agd_batch* b, const float* pos, const agd_forward_out* out, void* stream) {
+  int rc = check_ready(h, b);
+  if (rc) return rc;
+  if (!pos || !out) return fail(AGD_ERR_INVALID, "null argument");
+  if ((rc = enter(h, stream))) return rc;
+  LaunchCtx c = make_ctx(h);
+  run_global_branch(c, b->d, h->w, pos);
+  run_local_branch(c, b->d, h->w, pos, nullptr);
+  launch_export_edges(c, b->d, *out, true);
+  return leave(h, stream);
+}
+
+int agd_sample(agd_handle* h, agd_batch* b, float* pos, const agd_sample_params* p, int32_t* first_nan_step, void* stream) {
+  int rc = check_ready(h, b);
+  if (rc) return rc;
+  if (!pos || !p || p->n_steps < 0) return fail(AGD_ERR_INVALID, "bad sampler arguments");
+  if (first_nan_step) *first_nan_step = -1;
+  if (p->n_steps == 0) return AGD_OK;
+  if ((rc = enter(h, stream))) return rc;
+  BatchDev& d = b->d;
+  // per-step schedule -> device
+  if (d.sched_cap < p->n_steps) {
+    if (d.sched) CUDA_TRY(cudaFree(d.sched));
+    d.sched = nullptr;
+    CUDA_TRY(cudaMalloc(&d.sched, sizeof(float) * 4 * (size_t)p->n_steps));
+    d.sched_cap = p->n_steps;
+  }
+  std::vector<float> sched(4 * (size_t)p->n_steps);
+  for (int s = 0; s < p->n_steps; ++s) {
+    sched[4 * s + 0] = p->sigma[s];
+    sched[4 * s + 1] = p->step_size[s];
+    sched[4 * s + 2] = p->noise_scale[s];
+    sched[4 * s + 3] = p->use_global[s] ? 1.f : 0.f;
+  }
+  CUDA_TRY(cudaMemcpyAsync(d.sched, sched.data(), sizeof(float) * sched.size(), cudaMemcpyHostToDevice, h->stream));
+  const int init[4] = {0, 0, INT_MAX, 0};
+  CUDA_TRY(cudaMemcpyAsync(d.counters, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));  // `sched`/`init` are stack/heap temporaries
+
+  LaunchCtx c = make_ctx(h);
+  StepParams sp;
+  sp.w_global = p->w_global; sp.clip = p->clip; sp.clip_local = p->clip_local; sp.clip_pos = p->clip_pos;
+  sp.seed = p->seed; sp.noise = p->noise; sp.traj = p->traj; sp.step_offset = p->step_offset;
+  auto one_step = [&](bool use_global) {
+    if (use_global) run_global_branch(c, d, h->w, pos);
+    run_local_branch(c, d, h->w, pos, nullptr);
+    sp.use_global = use_global ? 1 : 0;
+    launch_step(c, d, pos, sp);
+    launch_advance(c, d);
+  };
+  bool any_global = false, any_local = false;
+  for (int s = 0; s < p->n_steps; ++s) (p->use_global[s] ? any_global : any_local) = true;
+
+  if (p->use_cuda_graph) {
+    cudaGraphExec_t exec[2] = {nullptr, nullptr};
+    int64_t per_graph_launches[2] = {0, 0};
+    for (int g = 0; g < 2; ++g) {
+      if (!(g ? any_global : any_local)) continue;
+      cudaGraph_t graph = nullptr;
+      const int64_t before = h->launches;
+      CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      one_step(g == 1);
+      cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+      per_graph_launches[g] = h->launches - before;
+      h->launches = before;
+      if (e != cudaSuccess) return fail(AGD_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&exec[g], graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) return fail(AGD_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+    }
+    cudaError_t e = cudaSuccess;
+    for (int s = 0; s < p->n_steps && e == cudaSuccess; ++s) {
+      const int g = p->use_global[s] ? 1 : 0;
+      e = cudaGraphLaunch(exec[g], h->stream);
+      h->launches += per_graph_launches[g];
+    }
+    cudaError_t e2 = cudaStreamSynchronize(h->stream);
+    for (int g = 0; g < 2; ++g)
+      if (exec[g]) cudaGraphExecDestroy(exec[g]);
+    if (e != cudaSuccess) return fail(AGD_ERR_CUDA, std::string("graph launch: ") + cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return fail(AGD_ERR_CUDA, std::string("sampling loop: ") + cudaGetErrorString(e2));
+  } else {
+    for (int s = 0; s < p->n_steps; ++s) one_step(p->use_global[s] != 0);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  CUDA_TRY(cudaGetLastError());
+  if ((rc = check_overflow(b))) return rc;
+  int nan_step = INT_MAX;
+  CUDA_TRY(cudaMemcpy(&nan_step, d.counters + 2, sizeof(int), cudaMemcpyDeviceToHost));
+  if ((rc = leave(h, stream))) return rc;
+  if (nan_step != INT_MAX) {
+    if (first_nan_step) *first_nan_step = nan_step;
+    return fail(AGD_ERR_NAN, "NaN positions at sampling step " + std::to_string(nan_step));
+  }
+  return AGD_OK;
+}
+
+int agd_extend_bond_order(const int32_t* mol_ptr, int32_t n_mols, int32_t n_atoms, const int32_t* bond_ptr,
+                          const int32_t* bond_dst, const int32_t* bond_type, int32_t order, int32_t num_bond_types,
+                          int32_t* out_count, const int32_t* out_ptr, int32_t* out_dst, int32_t* out_type, void* stream) {
+  if (!mol_ptr || !bond_ptr || n_mols <= 0) return fail(AGD_ERR_INVALID, "bad arguments");
+  if (!out_ptr && !out_count) return fail(AGD_ERR_INVALID, "count pass needs out_count");
+  int rc = launch_extend_bond_order((cudaStream_t)stream, mol_ptr, n_mols, n_atoms, bond_ptr, bond_dst, bond_type, order,
+                                    num_bond_types, out_count, out_ptr, out_dst, out_type);
+  if (rc) return fail(rc, "edge order must be 1..3");
+  CUDA_TRY(cudaGetLastError());
+  return AGD_OK;
+}
+
+int agd_op_cfconv_aggregate(const float* x, const float* W, const int32_t* src, const int32_t* in_ptr, int32_t n_nodes,
+                            int32_t F, float* out, void* stream) {
+  if (F != 64 && F != 128 && F != 192) return fail(AGD_ERR_INVALID, "F must be 64, 128 or 192");
+  int64_t dummy = 0;
+  LaunchCtx c{};
+  c.stream = (cudaStream_t)stream;
+  c.launch_counter = &dummy;
+  launch_aggregate(c, x, W, src, in_ptr, n_nodes, F, out);
+  CUDA_TRY(cudaGetLastError());
+  return AGD_OK;
+}
+
+int agd_op_eq_transform(const float* score, const float* pos, const int32_t* src, const int32_t* dst, const float* length,
+                        int64_t n_edges, int32_t n_nodes, float* out, void* stream) {
+  launch_eq_transform((cudaStream_t)stream, score, pos, src, dst, length, n_edges, n_nodes, out);
+  CUDA_TRY(cudaGetLastError());
+  return AGD_OK;
+}
+
+int64_t agd_debug_fetch(agd_batch* b, const char* name, float* dst, int64_t capacity) {
+  if (!b || !name || !dst) return fail(AGD_ERR_INVALID, "null argument");
+  const BatchDev& d = b->d;
+  cudaSetDevice(b->h->cfg.device);
+  cudaStreamSynchronize(b->h->stream);
+  int n_edges = 0;
+  cudaMemcpy(&n_edges, d.counters, sizeof(int), cudaMemcpyDeviceToHost);
+  const float* src = nullptr;
+  int64_t n = 0;
+  const std::string s(name);
+  if (s == "g2") { src = d.g2; n = (int64_t)n_edges * HID; }
+  else if (s == "filt") { src = d.filt; n = (int64_t)n_edges * 192; }
+  else if (s == "h_global") { src = d.h; n = (int64_t)d.n_atoms * HID; }
+  else if (s == "xcat") { src = d.xcat; n = (int64_t)d.n_atoms * 192; }
+  else if (s == "agg") { src = d.agg; n = (int64_t)d.n_atoms * 192; }
+  else if (s == "ea_local") { src = d.ea_loc; n = (int64_t)d.n_local * HID; }
+  else if (s == "h_local") { src = (b->h->cfg.num_convs_local % 2) ? d.gx1 : d.gx0; n = (int64_t)d.n_atoms * HID; }
+  else if (s == "e_len") { src = d.e_len; n = n_edges; }
+  else if (s == "s_csc") { src = d.s_csc; n = n_edges; }
+  else return fail(AGD_ERR_INVALID, "unknown tensor name");
+  if (n > capacity) return fail(AGD_ERR_CAPACITY, "destination too small");
+  cudaError_t e = cudaMemcpy(dst, src, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice);
+  if (e != cudaSuccess) return fail(AGD_ERR_CUDA, cudaGetErrorString(e));
+  return n;
+}
+
+int64_t agd_launch_count(const agd_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,372 @@
+// Edge construction on device: radius graph (torch_cluster CUDA rule) united with the static
+// bond/higher-order edges, emitted both CSC-sorted (for the gather->scatter kernels) and in the
+// reference's canonical coalesced order (sorted by row*N+col; common.py:208-233), plus the
+// bond-order extension itself (common.py:135-205).  Integer work is bit-exact with the oracle:
+// the only floating-point decision is d2 < r*r, evaluated as (dx*dx + dy*dy) + dz*dz with
+// explicitly un-fused fp32 operations.
+//
+// One CTA owns one molecule (<= 256 atoms): its adjacency is a bit matrix in shared memory
+// (row i = sources of destination i) built by warp ballots, the transpose gives out-degrees and
+// canonical ranks by popcount, and a batch-wide exclusive scan turns per-atom degrees into CSC /
+// canonical segment pointers without any host-visible size.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace agd {
+
+constexpr int MAXA = AGD_MAX_MOL_ATOMS;
+
+__global__ void __launch_bounds__(128) adjacency_kernel(const float* __restrict__ pos, const int* __restrict__ mol_ptr,
+                                                        const int* __restrict__ st_src, const int* __restrict__ st_dst,
+                                                        const int* __restrict__ st_in_ptr, float r2,
+                                                        unsigned* __restrict__ adj, unsigned* __restrict__ adjT,
+                                                        int* __restrict__ in_deg, int* __restrict__ out_deg,
+                                                        int* __restrict__ counters) {
+  __shared__ float sp[MAXA * 3];
+  __shared__ unsigned A[MAXA * MAXW];
+  __shared__ unsigned AT[MAXA * MAXW];
+  const int m = blockIdx.x;
+  const int a0 = mol_ptr[m], a1 = mol_ptr[m + 1];
+  const int n = a1 - a0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  if (n > MAXA) {
+    if (tid == 0) counters[3] = 1;
+    return;
+  }
+  for (int i = tid; i < n * 3; i += blockDim.x) sp[i] = pos[(size_t)a0 * 3 + i];
+  for (int i = tid; i < n * MAXW; i += blockDim.x) {
+    A[i] = 0u;
+    AT[i] = 0u;
+  }
+  __syncthreads();
+  const int nw = (n + 31) >> 5;
+  for (int i = warp; i < n; i += nwarps) {
+    const float xi = sp[3 * i], yi = sp[3 * i + 1], zi = sp[3 * i + 2];
+    int cnt = 0;
+    for (int c = 0; c < nw; ++c) {
+      const int j = c * 32 + lane;
+      bool hit = false;
+      if (j < n) {
+        const float dx = __fsub_rn(sp[3 * j], xi), dy = __fsub_rn(sp[3 * j + 1], yi), dz = __fsub_rn(sp[3 * j + 2], zi);
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        hit = d2 < r2;
+      }
+      unsigned mask = __ballot_sync(0xffffffffu, hit);
+      const int rem = (AGD_MAX_RADIUS_NBRS + 1) - cnt;
+      if (__popc(mask) > rem) {  // keep only the `rem` lowest-index hits
+        unsigned t = mask;
+        for (int k = 0; k < rem; ++k) t &= t - 1;
+        mask &= ~t;
+      }
+      cnt += __popc(mask);
+      if (lane == 0) A[i * MAXW + c] = mask;
+      if (cnt >= AGD_MAX_RADIUS_NBRS + 1) break;
+    }
+    if (lane == 0) A[i * MAXW + (i >> 5)] &= ~(1u << (i & 31));  // loop=False: self removed afterwards
+  }
+  __syncthreads();
+  for (int e = st_in_ptr[a0] + tid; e < st_in_ptr[a1]; e += blockDim.x) {
+    const int i = st_dst[e] - a0, j = st_src[e] - a0;
+    atomicOr(&A[i * MAXW + (j >> 5)], 1u << (j & 31));
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * nw; idx += blockDim.x) {
+    const int i = idx / nw, c = idx - i * nw;
+    unsigned bits = A[i * MAXW + c];
+    while (bits) {
+      const int j = c * 32 + (__ffs(bits) - 1);
+      atomicOr(&AT[j * MAXW + (i >> 5)], 1u << (i & 31));
+      bits &= bits - 1;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n * MAXW; i += blockDim.x) {
+    adj[(size_t)a0 * MAXW + i] = A[i];
+    adjT[(size_t)a0 * MAXW + i] = AT[i];
+  }
+  for (int i = tid; i < n; i += blockDim.x) {
+    int di = 0, dout = 0;
+#pragma unroll
+    for (int c = 0; c < MAXW; ++c) {
+      di += __popc(A[i * MAXW + c]);
+      dout += __popc(AT[i * MAXW + c]);
+    }
+    in_deg[a0 + i] = di;
+    out_deg[a0 + i] = dout;
+  }
+}
+
+// exclusive scans of the two degree arrays (single CTA; N is a few 1e5 at most per batch chunk)
+__global__ void __launch_bounds__(1024) degree_scan_kernel(const int* __restrict__ in_deg, const int* __restrict__ out_deg,
+                                                           int n, int* __restrict__ in_ptr, int* __restrict__ out_ptr,
+                                                           int* __restrict__ counters) {
+  __shared__ int ws[2][32];
+  __shared__ int tot[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int carry0 = 0, carry1 = 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const int v0 = (i < n) ? in_deg[i] : 0, v1 = (i < n) ? out_deg[i] : 0;
+    int s0 = v0, s1 = v1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o);
+      if (lane >= o) {
+        s0 += t0;
+        s1 += t1;
+      }
+    }
+    if (lane == 31) {
+      ws[0][warp] = s0;
+      ws[1][warp] = s1;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int w0 = ws[0][lane], w1 = ws[1][lane];
+      int p0 = w0, p1 = w1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t0 = __shfl_up_sync(0xffffffffu, p0, o), t1 = __shfl_up_sync(0xffffffffu, p1, o);
+        if (lane >= o) {
+          p0 += t0;
+          p1 += t1;
+        }
+      }
+      ws[0][lane] = p0 - w0;  // exclusive warp offsets
+      ws[1][lane] = p1 - w1;
+      if (lane == 31) {
+        tot[0] = p0;
+        tot[1] = p1;
+      }
+    }
+    __syncthreads();
+    if (i < n) {
+      in_ptr[i] = carry0 + ws[0][warp] + s0 - v0;
+      out_ptr[i] = carry1 + ws[1][warp] + s1 - v1;
+    }
+    carry0 += tot[0];
+    carry1 += tot[1];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    in_ptr[n] = carry0;
+    out_ptr[n] = carry1;
+    counters[0] = carry0;
+  }
+}
+
+// one warp per destination atom: emit its in-edges (sources ascending) into the CSC arrays and
+// mirror every record to its canonical slot.
+__global__ void __launch_bounds__(256) edge_fill_kernel(const float* __restrict__ pos, const int* __restrict__ mol_ptr,
+                                                        const int* __restrict__ atom_mol, int n_atoms,
+                                                        const int* __restrict__ st_src, const int* __restrict__ st_type,
+                                                        const int* __restrict__ st_in_ptr, const unsigned* __restrict__ adj,
+                                                        const unsigned* __restrict__ adjT, const int* __restrict__ in_ptr,
+                                                        const int* __restrict__ out_ptr, int* __restrict__ e_src,
+                                                        int* __restrict__ e_dst, int* __restrict__ e_type,
+                                                        int* __restrict__ e_canon, float* __restrict__ e_len,
+                                                        int* __restrict__ c_src, int* __restrict__ c_dst,
+                                                        int* __restrict__ c_type, float* __restrict__ c_len) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n_atoms) return;
+  const int a0 = mol_ptr[atom_mol[i]];
+  const int il = i - a0;
+  const int base = in_ptr[i];
+  const int st0 = st_in_ptr[i], st1 = st_in_ptr[i + 1];
+  const float xi = pos[3 * (size_t)i], yi = pos[3 * (size_t)i + 1], zi = pos[3 * (size_t)i + 2];
+  int running = 0;
+#pragma unroll 1
+  for (int c = 0; c < MAXW; ++c) {
+    const unsigned bits = adj[(size_t)i * MAXW + c];
+    if (bits == 0u) continue;
+    if ((bits >> lane) & 1u) {
+      const int e = base + running + __popc(bits & ((1u << lane) - 1u));
+      const int j = a0 + c * 32 + lane;
+      int type = 0;
+      {
+        int lo = st0, hi = st1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (st_src[mid] < j) lo = mid + 1; else hi = mid;
+        }
+        if (lo < st1 && st_src[lo] == j) type = st_type[lo];
+      }
+      const float dx = pos[3 * (size_t)j] - xi, dy = pos[3 * (size_t)j + 1] - yi, dz = pos[3 * (size_t)j + 2] - zi;
+      const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+      int rank = 0;
+      const int wi = il >> 5;
+      for (int c2 = 0; c2 < wi; ++c2) rank += __popc(adjT[(size_t)j * MAXW + c2]);
+      rank += __popc(adjT[(size_t)j * MAXW + wi] & ((1u << (il & 31)) - 1u));
+      const int cp = out_ptr[j] + rank;
+      e_src[e] = j;
+      e_dst[e] = i;
+      e_type[e] = type;
+      e_len[e] = len;
+      e_canon[e] = cp;
+      c_src[cp] = j;
+      c_dst[cp] = i;
+      c_type[cp] = type;
+      c_len[cp] = len;
+    }
+    running += __popc(bits);
+  }
+}
+
+__global__ void export_edges_kernel(const int* __restrict__ counters, const int* __restrict__ c_src,
+                                    const int* __restrict__ c_dst, const int* __restrict__ c_type,
+                                    const float* __restrict__ c_len, const float* __restrict__ s_canon,
+                                    agd_forward_out out, int with_scores) {
+  const int n = counters[0];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    if (out.edge_row) out.edge_row[e] = c_src[e];
+    if (out.edge_col) out.edge_col[e] = c_dst[e];
+    if (out.edge_type) out.edge_type[e] = c_type[e];
+    if (out.edge_length) out.edge_length[e] = c_len[e];
+    if (with_scores && out.edge_inv_global) out.edge_inv_global[e] = s_canon[e];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && out.n_edges) out.n_edges[0] = n;
+}
+
+__global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+void launch_build_edges(const LaunchCtx& c, const BatchDev& b, const float* pos) {
+  const float r2 = c.cutoff * c.cutoff;
+  adjacency_kernel<<<b.n_mols, 128, 0, c.stream>>>(pos, b.mol_ptr, b.st_src, b.st_dst, b.st_in_ptr, r2, b.adj, b.adjT,
+                                                   b.in_deg, b.out_deg, b.counters);
+  degree_scan_kernel<<<1, 1024, 0, c.stream>>>(b.in_deg, b.out_deg, b.n_atoms, b.in_ptr, b.out_ptr, b.counters);
+  const int warps_per_cta = 8;
+  edge_fill_kernel<<<(b.n_atoms + warps_per_cta - 1) / warps_per_cta, 256, 0, c.stream>>>(
+      pos, b.mol_ptr, b.atom_mol, b.n_atoms, b.st_src, b.st_type, b.st_in_ptr, b.adj, b.adjT, b.in_ptr, b.out_ptr,
+      b.e_src, b.e_dst, b.e_type, b.e_canon, b.e_len, b.c_src, b.c_dst, b.c_type, b.c_len);
+  *c.launch_counter += 3;
+}
+
+void launch_export_edges(const LaunchCtx& c, const BatchDev& b, const agd_forward_out& out, bool with_scores) {
+  int64_t blocks = (b.cap + 255) / 256;
+  if (blocks > c.num_sms * 8) blocks = c.num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  export_edges_kernel<<<(int)blocks, 256, 0, c.stream>>>(b.counters, b.c_src, b.c_dst, b.c_type, b.c_len, b.s_canon, out,
+                                                          with_scores ? 1 : 0);
+  *c.launch_counter += 1;
+  if (with_scores && out.edge_inv_local && b.n_local > 0) {
+    int64_t bl = (b.n_local + 255) / 256;
+    if (bl > c.num_sms * 8) bl = c.num_sms * 8;
+    copy_f32_kernel<<<(int)bl, 256, 0, c.stream>>>(b.sl_canon, out.edge_inv_local, b.n_local);
+    *c.launch_counter += 1;
+  }
+}
+
+// ------------------------------------------------------------------ bond-order extension
+// _extend_graph_order (common.py:135-205): pairs at shortest directed path length k in [2, order]
+// get type num_bond_types + k - 1; direct bonds keep the (summed) bond type; zero types vanish.
+// One CTA per molecule, reachability sets as bit rows.  out_ptr == nullptr: count pass.
+__global__ void __launch_bounds__(128) bond_order_kernel(const int* __restrict__ mol_ptr, const int* __restrict__ bond_ptr,
+                                                         const int* __restrict__ bond_dst,
+                                                         const int* __restrict__ bond_type, int order, int num_types,
+                                                         int* __restrict__ out_count, const int* __restrict__ out_ptr,
+                                                         int* __restrict__ out_dst, int* __restrict__ out_type) {
+  __shared__ unsigned R1[MAXA * MAXW];    // adj | I
+  __shared__ unsigned CUR[MAXA * MAXW];   // reach within k hops
+  __shared__ unsigned NXT[MAXA * MAXW];
+  __shared__ unsigned char HOP[MAXA * MAXA / 4];  // 2 bits per pair would do; 0..3 packed 4 per byte
+  const int m = blockIdx.x;
+  const int a0 = mol_ptr[m], n = mol_ptr[m + 1] - a0;
+  const int tid = threadIdx.x;
+  if (n > MAXA || order > 3) return;  // guarded on the host
+  for (int i = tid; i < n * MAXW; i += blockDim.x) R1[i] = 0u;
+  for (int i = tid; i < (MAXA * MAXA / 4); i += blockDim.x) HOP[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    R1[i * MAXW + (i >> 5)] |= 1u << (i & 31);
+    for (int e = bond_ptr[a0 + i]; e < bond_ptr[a0 + i + 1]; ++e) {
+      const int j = bond_dst[e] - a0;
+      R1[i * MAXW + (j >> 5)] |= 1u << (j & 31);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n * MAXW; i += blockDim.x) CUR[i] = R1[i];
+  __syncthreads();
+  // hop 1 marks
+  for (int i = tid; i < n; i += blockDim.x)
+    for (int c = 0; c < MAXW; ++c) {
+      unsigned bits = R1[i * MAXW + c];
+      while (bits) {
+        const int j = c * 32 + (__ffs(bits) - 1);
+        bits &= bits - 1;
+        if (j != i) {
+          const int p = i * MAXA + j;
+          HOP[p >> 2] |= (unsigned char)(1u << ((p & 3) * 2));   // row i is owned by this thread only
+        }
+      }
+    }
+  __syncthreads();
+  for (int k = 2; k <= order; ++k) {
+    for (int i = tid; i < n; i += blockDim.x) {
+      unsigned acc[MAXW];
+#pragma unroll
+      for (int c = 0; c < MAXW; ++c) acc[c] = 0u;
+      for (int c = 0; c < MAXW; ++c) {
+        unsigned bits = CUR[i * MAXW + c];
+        while (bits) {
+          const int j = c * 32 + (__ffs(bits) - 1);
+          bits &= bits - 1;
+#pragma unroll
+          for (int c2 = 0; c2 < MAXW; ++c2) acc[c2] |= R1[j * MAXW + c2];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < MAXW; ++c) {
+        NXT[i * MAXW + c] = acc[c];
+        unsigned fresh = acc[c] & ~CUR[i * MAXW + c];
+        while (fresh) {
+          const int j = c * 32 + (__ffs(fresh) - 1);
+          fresh &= fresh - 1;
+          const int p = i * MAXA + j;
+          HOP[p >> 2] |= (unsigned char)((unsigned)k << ((p & 3) * 2));
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < n * MAXW; i += blockDim.x) CUR[i] = NXT[i];
+    __syncthreads();
+  }
+  // emit: thread per source atom, destinations ascending.  Candidates = reachable set | direct bonds.
+  for (int i = tid; i < n; i += blockDim.x) {
+    int cnt = 0;
+    const int o = out_ptr ? out_ptr[a0 + i] : 0;
+    for (int j = 0; j < n; ++j) {
+      const int p = i * MAXA + j;
+      const int hop = (HOP[p >> 2] >> ((p & 3) * 2)) & 3;
+      int t = 0;
+      const bool direct = (R1[i * MAXW + (j >> 5)] >> (j & 31)) & 1u;
+      if (direct)
+        for (int e = bond_ptr[a0 + i]; e < bond_ptr[a0 + i + 1]; ++e)
+          if (bond_dst[e] - a0 == j) t += bond_type[e];
+      if (hop > 1) t += num_types + hop - 1;
+      if (t != 0) {
+        if (out_ptr) {
+          out_dst[o + cnt] = a0 + j;
+          out_type[o + cnt] = t;
+        }
+        ++cnt;
+      }
+    }
+    if (!out_ptr) out_count[a0 + i] = cnt;
+  }
+}
+
+int launch_extend_bond_order(cudaStream_t s, const int* mol_ptr, int n_mols, int n_atoms, const int* bond_ptr,
+                             const int* bond_dst, const int* bond_type, int order, int num_bond_types, int* out_count,
+                             const int* out_ptr, int* out_dst, int* out_type) {
+  if (order > 3 || order < 1) return AGD_ERR_INVALID;
+  (void)n_atoms;
+  bond_order_kernel<<<n_mols, 128, 0, s>>>(mol_ptr, bond_ptr, bond_dst, bond_type, order, num_bond_types, out_count,
+                                           out_ptr, out_dst, out_type);
+  return AGD_OK;
+}
+
+}  // namespace agd

@@ -1,0 +1,131 @@
+// Host-side declarations shared by the translation units of libagdiff_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/agdiff_b200.h"
+
+namespace agd {
+
+constexpr int MAX_BLOCKS = 8;   // SchNet interaction blocks supported (reference config: 6)
+constexpr int MAX_GIN = 8;      // GIN layers supported (reference config: 4)
+
+// ------------------------------------------------------------------ packed weights (device pointers)
+// All matrices are [K][N] row-major (= torch weight transposed), BatchNorm(eval) folded, and
+// back-to-back Linears merged by the host mirror (agdiff_b200/pack.py) in fp64.
+struct EncW {              // MLPEdgeEncoder edge.py:84-103 (the *global* instance serves both branches)
+  const float *fe_w, *fe_b;   // [128] feature_expansion
+  const float *T1, *W1;       // [100][128] per-type table (bond half of edge_feature_mlp.0 + bias), [128][128]
+  const float *T2, *M2;       // [100][128] table, [128][128] = combination_mlp.0[:, :128] @ edge_feature_mlp.2
+  const float *C2, *c2b;      // combination_mlp.2 (only the local branch materialises edge_attr)
+};
+struct BlkW {              // InteractionBlock k, schnet.py:165-216 (+ scaling module :219-234)
+  const float *L1a, *l1ab, *L1b, *l1bb;      // conv{1,2}.lin1 with norm1 folded: [128][128], [128][64]
+  const float *F1a, *f1ab, *F2a, *f2ab;      // conv1.nn: first layer merged with the encoder's last Linear
+  const float *F1b, *f1bb, *F2b, *f2bb;      // conv2.nn: [128][64], [64][64]
+  const float *dw1, *dw2;                    // distance_weighting packs [w1|b1|w2|b2] (100 floats used)
+  const float *L2a, *l2ab, *L2b, *l2bb;      // conv{1,2}.lin2 with norm2 folded: [128][128], [64][128]
+  const float *LIN, *linb;                   // lin: [256][128]
+  const float *A1, *a1b, *a2w;               // attention: [128][64], [64], [64]
+  const float *S1, *S2;                      // scaling fc: [128][8], [8][128]
+  const float *sc;                           // scalars: beta(conv1.nn.1), beta(conv2.nn.1), beta(act), attention.2.bias
+};
+struct PairW {             // grad_{global,local}_dist_mlp, common.py:86-103 on [h_row*h_col, edge_attr]
+  const float *P1h, *P1e, *p1b;   // layers.0 split: [128][128] on h_row*h_col, [128][128] on g2 (global, merged) / edge_attr (local)
+  const float *P2, *p2b;          // [128][64]
+  const float *p3w, *p3b;         // [64], [1]
+};
+struct GinW {              // GINEConv + BatchNorm, gin.py:38-69,112-148
+  const float *G1, *g1b, *G2, *g2b;   // nn.layers.0, nn.layers.1 with batch_norm folded
+  const float* sc;                    // [1 + eps]
+};
+struct ModelW {
+  EncW enc;
+  const float* sch_emb;   // [100][128], max_norm renorm pre-applied
+  BlkW blk[MAX_BLOCKS];
+  PairW pg, pl;
+  const float* gin_emb;   // [100][128]
+  GinW gin[MAX_GIN];
+};
+
+// ------------------------------------------------------------------ per-batch device state
+struct BatchDev {
+  int n_atoms, n_mols, n_static, n_local;
+  int64_t cap;
+  // topology (caller-owned)
+  const int *atom_type, *mol_ptr, *atom_mol;
+  const int64_t* mol_gid;
+  const int *st_src, *st_dst, *st_type, *st_in_ptr;
+  const int *lc_src, *lc_dst, *lc_type, *lc_in_ptr, *lc_canon, *lc_out_ptr, *lc_cdst;
+  // edge builder scratch
+  unsigned *adj, *adjT;          // [N][MAXW]
+  int *in_deg, *out_deg;         // [N]
+  int *in_ptr, *out_ptr;         // [N+1]
+  int* counters;                 // [0]=n_edges [1]=step index [2]=first NaN step
+  // radius-extended edges, CSC order (grouped by destination)
+  int *e_src, *e_dst, *e_type, *e_canon;
+  float* e_len;
+  // the same edges in canonical (row-major) order
+  int *c_src, *c_dst, *c_type;
+  float* c_len;
+  float *s_csc, *s_canon;        // edge_inv_global
+  // local edges
+  float *lc_len, *lcc_len;       // CSC / canonical
+  float *sl_csc, *sl_canon;      // edge_inv_local
+  float* ea_loc;                 // [n_local][128]
+  // activations
+  float* g2;                     // [cap][128]  encoder hidden state feeding filters and the pair MLP
+  float* filt;                   // [cap][192]  CFConv filters of the current block (conv1 | conv2)
+  float *h, *xcat, *agg;         // [N][128], [N][192], [N][192]
+  float *gx0, *gx1;              // [N][128] GIN ping-pong
+  // per-step schedule (device copy)
+  float* sched;                  // [n_steps][4] sigma, step_size, noise_scale, use_global
+  int sched_cap;
+};
+
+struct StepParams {
+  float w_global, clip, clip_local, clip_pos;
+  uint64_t seed;
+  const float* noise;
+  float* traj;
+  int use_global;   // which per-step graph this launch belongs to
+  int step_offset;  // added to the device step counter for the Philox stream
+};
+
+struct LaunchCtx {
+  cudaStream_t stream;
+  int num_sms;
+  int64_t* launch_counter;
+  float cutoff;
+  int smooth;
+  int num_convs, num_convs_local;
+};
+
+// edges.cu
+void launch_build_edges(const LaunchCtx& c, const BatchDev& b, const float* pos);
+void launch_export_edges(const LaunchCtx& c, const BatchDev& b, const agd_forward_out& out, bool with_scores);
+int launch_extend_bond_order(cudaStream_t s, const int* mol_ptr, int n_mols, int n_atoms, const int* bond_ptr,
+                             const int* bond_dst, const int* bond_type, int order, int num_bond_types, int* out_count,
+                             const int* out_ptr, int* out_dst, int* out_type);
+// encoder.cu
+void launch_encoder_global(const LaunchCtx& c, const BatchDev& b, const ModelW& w);
+void launch_encoder_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos);
+void launch_pair_global(const LaunchCtx& c, const BatchDev& b, const ModelW& w);
+void launch_pair_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* h_local);
+// schnet.cu
+void launch_filters(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);
+void launch_aggregate(const LaunchCtx& c, const float* x, const float* W, const int* src, const int* in_ptr, int n_nodes,
+                      int F, float* out);
+void launch_schnet_node(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk /* -1: embedding + first lin1 */);
+// gin.cu
+void launch_gin_embed(const LaunchCtx& c, const BatchDev& b, const ModelW& w);
+void launch_gin_layer(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int layer, const float* x_in, float* x_out);
+// step.cu
+void launch_step(const LaunchCtx& c, const BatchDev& b, float* pos, const StepParams& p);
+void launch_advance(const LaunchCtx& c, const BatchDev& b);
+void launch_eq_transform(cudaStream_t s, const float* score, const float* pos, const int* src, const int* dst,
+                         const float* len, int64_t n_edges, int n_nodes, float* out);
+
+void set_kernel_attributes();   // opt-in dynamic shared memory sizes; called once per process
+
+}  // namespace agd

@@ -1,0 +1,574 @@
+"""Drop-in for the reference's ``agdiff.models.epsnet`` on the sampling path.
+
+``get_model(config)`` and ``DualEncoderEpsNetwork`` keep the reference's constructor, ``forward``
+and sampler signatures, ``configs/*.yml`` ``model:`` fields and ``state_dict`` keys
+(reference src/agdiff/models/epsnet/__init__.py:4-8, dualenc.py:54-251,397-547), but the
+computation is done by hand-written sm_100a kernels behind the C ABI in
+``include/agdiff_b200.h``.  The ``nn.Module`` tree below only *holds parameters* (created in the
+reference's construction order, so the same ``torch.manual_seed`` gives the same random init and
+``load_state_dict`` of a reference checkpoint works unchanged); it has no PyTorch compute path
+and no CPU fallback.
+
+Extensions (keyword-only, all optional, defaults reproduce the reference behaviour):
+  noise=(n_steps,N,3) tensor   inject the Langevin noise instead of drawing it (parity tests)
+  seed=int                     Philox seed for the device noise generator
+  return_traj=bool             False skips the per-step trajectory (reference always keeps it)
+  mol_gid=(G,) int64           global molecule ids keying the noise streams (multi-GPU sharding)
+  use_cuda_graph=bool          replay captured per-step graphs (default True)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .pack import fold_state_dict, pack
+
+NUM_BOND_TYPES = 22  # len(BOND_TYPES), reference src/agdiff/utils/chem.py:17
+
+
+# --------------------------------------------------------------------------------------------
+# parameter containers (construction order == reference, see module docstring)
+# --------------------------------------------------------------------------------------------
+def _box(children) -> nn.Module:
+    m = nn.Module()
+    for name, child in children:
+        m.add_module(name, child)
+    return m
+
+
+class _Beta(nn.Module):
+    """holder of ShiftedSoftplus.beta (reference schnet.py:71-80)"""
+
+    def __init__(self):
+        super().__init__()
+        self.beta = nn.Parameter(torch.tensor(1.0))
+
+
+class _Eps(nn.Module):
+    """GINEConv: buffer eps + its MLP (reference gin.py:14-36)"""
+
+    def __init__(self, hidden):
+        super().__init__()
+        self.nn = _box([("layers", nn.ModuleList([nn.Linear(hidden, hidden), nn.Linear(hidden, hidden)])),
+                        ("attention_layers", nn.ModuleList())])
+        self.register_buffer("eps", torch.Tensor([0.0]))
+
+
+class _AttnW(nn.Module):
+    """CFConv.attention (constructed, never evaluated: reference schnet.py:103-110,126)"""
+
+    def __init__(self, n):
+        super().__init__()
+        self.attention_weights = nn.Parameter(torch.randn(n))
+
+
+def _edge_encoder(hidden) -> nn.Module:
+    # reference edge.py:45-82
+    return _box([
+        ("bond_emb", nn.Embedding(100, hidden)),
+        ("feature_expansion", nn.Linear(1, hidden)),
+        ("edge_feature_mlp", _box([("0", nn.Linear(2 * hidden, hidden)), ("2", nn.Linear(hidden, hidden))])),
+        ("combination_mlp", _box([("0", nn.Linear(2 * hidden, hidden)), ("2", nn.Linear(hidden, hidden))])),
+        ("attention", _box([("0", nn.Linear(hidden, hidden)), ("2", nn.Linear(hidden, 1))])),
+    ])
+
+
+def _cfconv(in_ch, out_ch, filters, filter_net) -> nn.Module:
+    # reference schnet.py:113-134 (submodule creation order, then reset_parameters)
+    lin1 = nn.Linear(in_ch, filters)
+    norm1 = nn.BatchNorm1d(filters)
+    lin2 = nn.Linear(filters, out_ch)
+    norm2 = nn.BatchNorm1d(out_ch)
+    attention = _AttnW(filters)
+    dw = _box([("layer1", nn.Linear(1, 32)), ("layer2", nn.Linear(32, 1))])
+    nn.init.xavier_uniform_(lin1.weight)
+    lin1.bias.data.fill_(0)
+    nn.init.xavier_uniform_(lin2.weight)
+    lin2.bias.data.fill_(0)
+    return _box([("lin1", lin1), ("norm1", norm1), ("lin2", lin2), ("norm2", norm2), ("nn", filter_net),
+                 ("attention", attention), ("distance_weighting", dw)])
+
+
+def _interaction(hidden, edge_ch, filters) -> nn.Module:
+    # reference schnet.py:165-199
+    mlp1 = _box([("0", nn.Linear(edge_ch, filters)), ("1", _Beta()), ("2", nn.Linear(filters, filters))])
+    mlp2 = _box([("0", nn.Linear(edge_ch, filters // 2)), ("1", _Beta()), ("2", nn.Linear(filters // 2, filters // 2))])
+    conv1 = _cfconv(hidden, hidden, filters, mlp1)
+    conv2 = _cfconv(hidden, hidden, filters // 2, mlp2)
+    act = _Beta()
+    lin = nn.Linear(256, hidden)
+    att = _box([("0", nn.Linear(hidden, hidden // 2)), ("2", nn.Linear(hidden // 2, 1))])
+    return _box([("conv1", conv1), ("conv2", conv2), ("act", act), ("lin", lin), ("attention", att)])
+
+
+def _schnet(hidden, num_interactions, edge_ch) -> nn.Module:
+    # reference schnet.py:237-266
+    emb = nn.Embedding(100, hidden, max_norm=10.0)
+    inter, scal = nn.ModuleList(), nn.ModuleList()
+    for _ in range(num_interactions):
+        inter.append(_interaction(hidden, edge_ch, hidden))
+        scal.append(_box([("fc", _box([("0", nn.Linear(hidden, hidden // 16, bias=False)),
+                                      ("2", nn.Linear(hidden // 16, hidden, bias=False))]))]))
+    return _box([("embedding", emb), ("interactions", inter), ("scaling_modules", scal)])
+
+
+def _gin(hidden, num_convs) -> nn.Module:
+    # reference gin.py:75-110
+    emb = nn.Embedding(100, hidden)
+    convs, bns = nn.ModuleList(), nn.ModuleList()
+    for _ in range(num_convs):
+        convs.append(_Eps(hidden))
+        bns.append(nn.BatchNorm1d(hidden))
+    return _box([("node_emb", emb), ("convs", convs), ("batch_norms", bns)])
+
+
+def _pair_mlp(hidden) -> nn.Module:
+    # reference common.py:44-84 with dims [2H, H, H/2, 1]
+    dims = [2 * hidden, hidden, hidden // 2, 1]
+    return _box([("layers", nn.ModuleList([nn.Linear(dims[i], dims[i + 1]) for i in range(3)])),
+                 ("attention_layers", nn.ModuleList())])
+
+
+def get_beta_schedule(beta_schedule, *, beta_start, beta_end, num_diffusion_timesteps):
+    """float64 numpy schedule, reference dualenc.py:21-51."""
+    T = num_diffusion_timesteps
+    if beta_schedule == "quad":
+        betas = np.linspace(beta_start ** 0.5, beta_end ** 0.5, T, dtype=np.float64) ** 2
+    elif beta_schedule == "linear":
+        betas = np.linspace(beta_start, beta_end, T, dtype=np.float64)
+    elif beta_schedule == "const":
+        betas = beta_end * np.ones(T, dtype=np.float64)
+    elif beta_schedule == "jsd":
+        betas = 1.0 / np.linspace(T, 1, T, dtype=np.float64)
+    elif beta_schedule == "sigmoid":
+        x = np.linspace(-6, 6, T)
+        betas = 1 / (np.exp(-x) + 1) * (beta_end - beta_start) + beta_start
+    else:
+        raise NotImplementedError(beta_schedule)
+    assert betas.shape == (T,)
+    return betas
+
+
+# --------------------------------------------------------------------------------------------
+# native batch (topology + workspace)
+# --------------------------------------------------------------------------------------------
+def _i32(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.int32).contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _csr_ptr(idx: torch.Tensor, n: int) -> torch.Tensor:
+    ptr = torch.zeros(n + 1, dtype=torch.long, device=idx.device)
+    if idx.numel():
+        ptr[1:] = torch.cumsum(torch.bincount(idx, minlength=n), 0)
+    return ptr
+
+
+class NativeBatch:
+    """Device topology of one (sub-)batch plus the library workspace handle."""
+
+    def __init__(self, model: "DualEncoderEpsNetwork", atom_type, st_row, st_col, st_type, batch, mol_gid=None):
+        lib = _lib.load()
+        dev = atom_type.device
+        N = int(atom_type.numel())
+        self.N = N
+        if N == 0:
+            raise ValueError("empty batch")
+        if batch.numel() != N:
+            raise ValueError("batch and atom_type disagree")
+        if N > 1 and bool((batch[1:] < batch[:-1]).any()):
+            raise ValueError("`batch` must be sorted (molecules contiguous), as PyG batches are")
+        G = int(batch[-1].item()) + 1
+        self.G = G
+        counts = torch.bincount(batch, minlength=G)
+        if int(counts.max().item()) > _lib.MAX_MOL_ATOMS:
+            raise NotImplementedError("molecules with more than %d atoms are not supported by the "
+                                      "bit-matrix edge builder" % _lib.MAX_MOL_ATOMS)
+        mol_ptr = torch.zeros(G + 1, dtype=torch.long, device=dev)
+        mol_ptr[1:] = torch.cumsum(counts, 0)
+        if int(atom_type.max().item()) >= 100 or int(atom_type.min().item()) < 0:
+            raise IndexError("atom_type out of range for Embedding(100, ...)")
+        if st_type.numel() and (int(st_type.max().item()) >= 100 or int(st_type.min().item()) < 0):
+            raise IndexError("edge_type out of range for Embedding(100, ...)")
+        if st_row.numel() and bool((batch[st_row] != batch[st_col]).any()):
+            raise ValueError("bond_index connects atoms of different molecules")
+        # canonical static list (sorted by row*N+col) -> CSC (sorted by col*N+row)
+        perm = torch.argsort(st_col * N + st_row)
+        self.st_src, self.st_dst, self.st_type = _i32(st_row[perm]), _i32(st_col[perm]), _i32(st_type[perm])
+        st_in = _csr_ptr(st_col, N)
+        self.st_in_ptr = _i32(st_in)
+        lmask = st_type > 0
+        if bool(lmask.all()):
+            l_row, l_col, l_type, lperm = st_row, st_col, st_type, perm
+        else:
+            l_row, l_col, l_type = st_row[lmask], st_col[lmask], st_type[lmask]
+            lperm = torch.argsort(l_col * N + l_row)
+        self.n_local = int(l_row.numel())
+        self.lc_src, self.lc_dst, self.lc_type = _i32(l_row[lperm]), _i32(l_col[lperm]), _i32(l_type[lperm])
+        self.lc_in_ptr = _i32(_csr_ptr(l_col, N))
+        self.lc_canon = _i32(lperm)
+        self.lc_out_ptr = _i32(_csr_ptr(l_row, N))
+        self.lc_cdst = _i32(l_col)
+        self.l_row, self.l_col = l_row, l_col
+        # capacity: in-degree <= min(n_mol, 33 + static in-degree)
+        n_of_atom = counts[batch]
+        cap = torch.minimum(n_of_atom, (st_in[1:] - st_in[:-1]) + (_lib.MAX_RADIUS_NBRS + 1)).sum()
+        self.cap = int(cap.item())
+        self.atom_type = _i32(atom_type)
+        self.mol_ptr = _i32(mol_ptr)
+        self.atom_mol = _i32(batch)
+        self.batch = batch
+        if mol_gid is None:
+            mol_gid = torch.arange(G, dtype=torch.long, device=dev)
+        self.mol_gid = mol_gid.to(device=dev, dtype=torch.long).contiguous()
+        d = _lib.BatchDesc()
+        d.n_atoms, d.n_mols = N, G
+        d.atom_type, d.mol_ptr, d.atom_mol, d.mol_gid = (_ptr(self.atom_type), _ptr(self.mol_ptr),
+                                                        _ptr(self.atom_mol), _ptr(self.mol_gid))
+        d.n_static = int(st_row.numel())
+        d.st_src, d.st_dst, d.st_type, d.st_in_ptr = (_ptr(self.st_src), _ptr(self.st_dst), _ptr(self.st_type),
+                                                      _ptr(self.st_in_ptr))
+        d.n_local = self.n_local
+        d.lc_src, d.lc_dst, d.lc_type, d.lc_in_ptr = (_ptr(self.lc_src), _ptr(self.lc_dst), _ptr(self.lc_type),
+                                                      _ptr(self.lc_in_ptr))
+        d.lc_canon, d.lc_out_ptr, d.lc_cdst = _ptr(self.lc_canon), _ptr(self.lc_out_ptr), _ptr(self.lc_cdst)
+        d.edge_capacity = self.cap
+        self._desc = d
+        self._lib = lib
+        self.handle = C.c_void_p()
+        torch.cuda.synchronize(dev)  # topology tensors are complete before the library reads them
+        _lib.check(lib.agd_batch_create(model._native_handle(), C.byref(d), C.byref(self.handle)))
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self._lib.agd_batch_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def fetch(self, name: str, n_max: int) -> torch.Tensor:
+        out = torch.empty(n_max, dtype=torch.float32, device=self.atom_type.device)
+        n = self._lib.agd_debug_fetch(self.handle, name.encode(), _ptr(out), n_max)
+        if n < 0:
+            _lib.check(int(n))
+        return out[:n]
+
+
+# --------------------------------------------------------------------------------------------
+# the model
+# --------------------------------------------------------------------------------------------
+class DualEncoderEpsNetwork(nn.Module):
+    """Same constructor / forward / sampler contract as reference dualenc.py:54."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        if config.edge_encoder != "mlp":
+            # the reference's gaussian encoder raises NameError upstream (edge.py:25 uses an unimported class)
+            raise NotImplementedError("Unknown edge encoder: %s" % config.edge_encoder)
+        H = config.hidden_dim
+        self.edge_encoder_global = _edge_encoder(H)
+        self.edge_encoder_local = _edge_encoder(H)     # dead weights, kept for state_dict parity
+        self.encoder_global = _schnet(H, config.num_convs, H)
+        self.encoder_local = _gin(H, config.num_convs_local)
+        self.grad_global_dist_mlp = _pair_mlp(H)
+        self.grad_local_dist_mlp = _pair_mlp(H)
+        self.model_global = nn.ModuleList([self.edge_encoder_global, self.encoder_global, self.grad_global_dist_mlp])
+        self.model_local = nn.ModuleList([self.edge_encoder_local, self.encoder_local, self.grad_local_dist_mlp])
+        self.model_type = config.type
+        if self.model_type != "diffusion":
+            raise NotImplementedError("only model type 'diffusion' is on the sampling path (got %r)" % (config.type,))
+        betas = get_beta_schedule(beta_schedule=config.beta_schedule, beta_start=config.beta_start,
+                                  beta_end=config.beta_end, num_diffusion_timesteps=config.num_diffusion_timesteps)
+        betas = torch.from_numpy(betas).float()
+        self.betas = nn.Parameter(betas, requires_grad=False)
+        self.alphas = nn.Parameter((1.0 - betas).cumprod(dim=0), requires_grad=False)
+        self.num_timesteps = self.betas.size(0)
+        if H != 128:
+            raise NotImplementedError("hidden_dim is pinned to 128 (reference schnet.py:190-192)")
+        if getattr(config, "mlp_act", "relu") != "relu":
+            raise NotImplementedError("mlp_act=%r: the kernels implement the shipped configs' relu" % config.mlp_act)
+        self._handle = None
+        self._handle_device = None
+        self._packed_version = None
+
+    # ------------------------------------------------------------------ native plumbing
+    def _device(self) -> torch.device:
+        return self.betas.device
+
+    def _native_handle(self):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("agdiff_b200 runs on CUDA devices only (module is on %s); there is no CPU path" % dev)
+        lib = _lib.load()
+        if self._handle is None or self._handle_device != dev:
+            self._release()
+            cfg = _lib.Config(int(self.config.hidden_dim), int(self.config.num_convs), int(self.config.num_convs_local),
+                              1 if self.config.smooth_conv else 0, float(self.config.cutoff),
+                              dev.index if dev.index is not None else torch.cuda.current_device())
+            h = C.c_void_p()
+            _lib.check(lib.agd_create(C.byref(cfg), C.byref(h)))
+            self._handle, self._handle_device, self._packed_version = h, dev, None
+        return self._handle
+
+    def _release(self):
+        if self._handle is not None:
+            _lib.load().agd_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _weights_version(self):
+        return tuple(int(t._version) for t in list(self.parameters()) + list(self.buffers())) + (
+            tuple(int(t.data_ptr()) for t in self.parameters()),)
+
+    def _sync_weights(self):
+        """(re)pack and upload when any parameter/buffer changed since the last upload."""
+        h = self._native_handle()
+        ver = self._weights_version()
+        if ver == self._packed_version:
+            return
+        lib = _lib.load()
+        n = lib.agd_weight_slot_count(h)
+        names = [lib.agd_weight_slot_name(h, i).decode() for i in range(n)]
+        sizes = [int(lib.agd_weight_slot_size(h, i)) for i in range(n)]
+        folded = fold_state_dict(self.state_dict(), int(self.config.num_convs), int(self.config.num_convs_local))
+        buf, offs = pack(folded, names, sizes)
+        _lib.check(lib.agd_load_weights(h, buf.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), n, buf.size))
+        self._packed_version = ver
+
+    def launch_count(self) -> int:
+        return int(_lib.load().agd_launch_count(self._native_handle()))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self._device()).cuda_stream)
+
+    # ------------------------------------------------------------------ topology
+    def _static_edges(self, N, bond_index, bond_type, batch, extend_order):
+        """Canonical (sorted by row*N+col, duplicate types summed) static edge list; with
+        ``extend_order`` the 2-/3-hop edges are added on device (reference common.py:135-205)."""
+        dev = bond_index.device
+        row, col, typ = bond_index[0].long(), bond_index[1].long(), bond_type.long()
+        key = row * N + col
+        if key.numel() > 1 and not bool((key[1:] > key[:-1]).all()):
+            uniq, inv = torch.unique(key, sorted=True, return_inverse=True)
+            tsum = torch.zeros(uniq.numel(), dtype=torch.long, device=dev).index_add_(0, inv, typ)
+            row, col, typ = uniq // N, uniq % N, tsum
+        if not extend_order:
+            return row, col, typ
+        order = int(self.config.edge_order)
+        lib = _lib.load()
+        G = int(batch[-1].item()) + 1
+        counts = torch.bincount(batch, minlength=G)
+        if int(counts.max().item()) > _lib.MAX_MOL_ATOMS:
+            raise NotImplementedError("molecules with more than %d atoms are not supported" % _lib.MAX_MOL_ATOMS)
+        mol_ptr = torch.zeros(G + 1, dtype=torch.long, device=dev)
+        mol_ptr[1:] = torch.cumsum(counts, 0)
+        mol_ptr32, bond_ptr32 = _i32(mol_ptr), _i32(_csr_ptr(row, N))
+        dst32, typ32 = _i32(col), _i32(typ)
+        cnt = torch.zeros(N, dtype=torch.int32, device=dev)
+        st = self._stream()
+        _lib.check(lib.agd_extend_bond_order(_ptr(mol_ptr32), G, N, _ptr(bond_ptr32), _ptr(dst32), _ptr(typ32), order,
+                                             NUM_BOND_TYPES, _ptr(cnt), None, None, None, st))
+        optr = torch.zeros(N + 1, dtype=torch.long, device=dev)
+        optr[1:] = torch.cumsum(cnt.long(), 0)
+        total = int(optr[-1].item())
+        optr32 = _i32(optr)
+        odst = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        otyp = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        _lib.check(lib.agd_extend_bond_order(_ptr(mol_ptr32), G, N, _ptr(bond_ptr32), _ptr(dst32), _ptr(typ32), order,
+                                             NUM_BOND_TYPES, None, _ptr(optr32), _ptr(odst), _ptr(otyp), st))
+        new_row = torch.repeat_interleave(torch.arange(N, device=dev), cnt.long())
+        return new_row, odst[:total].long(), otyp[:total].long()
+
+    def _prepare(self, atom_type, bond_index, bond_type, batch, extend_order, mol_gid=None) -> NativeBatch:
+        dev = self._device()
+        atom_type, batch = atom_type.to(dev), batch.to(dev)
+        bond_index, bond_type = bond_index.to(dev), bond_type.to(dev)
+        assert atom_type.dim() == 1 and atom_type.dtype == torch.long   # reference schnet.py:270
+        N = atom_type.numel()
+        row, col, typ = self._static_edges(N, bond_index, bond_type, batch, extend_order)
+        return NativeBatch(self, atom_type, row, col, typ, batch, mol_gid)
+
+    def _renorm_embedding(self, atom_type):
+        # side effect of nn.Embedding(max_norm=10) in the reference (schnet.py:254,271)
+        with torch.no_grad():
+            torch.embedding_renorm_(self.encoder_global.embedding.weight, atom_type.contiguous(), 10.0, 2.0)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, atom_type, pos, bond_index, bond_type, batch, time_step, edge_index=None, edge_type=None,
+                edge_length=None, return_edges=False, extend_order=True, extend_radius=True):
+        """reference dualenc.py:142-251; ``time_step`` is unused there as well."""
+        if edge_index is not None and edge_type is not None and edge_length is not None:
+            raise NotImplementedError("caller-supplied edge lists are not on the native path yet; pass None to have "
+                                      "them rebuilt (what every reference caller does)")
+        if not extend_radius:
+            raise NotImplementedError("extend_radius=False is not on the native path (no reference caller uses it)")
+        dev = self._device()
+        atom_type = atom_type.to(dev)
+        self._renorm_embedding(atom_type)
+        self._sync_weights()
+        nb = self._prepare(atom_type, bond_index, bond_type, batch, extend_order)
+        try:
+            res = self._forward_native(nb, pos)
+        finally:
+            nb.close()
+        return res if return_edges else res[:2]
+
+    def _forward_native(self, nb: NativeBatch, pos, build_only=False):
+        lib, dev = _lib.load(), self._device()
+        pos = pos.to(dev, torch.float32).contiguous()
+        cap = max(nb.cap, 1)
+        eg = torch.empty(cap, dtype=torch.float32, device=dev)
+        el = torch.empty(max(nb.n_local, 1), dtype=torch.float32, device=dev)
+        erow = torch.empty(cap, dtype=torch.int32, device=dev)
+        ecol = torch.empty(cap, dtype=torch.int32, device=dev)
+        etyp = torch.empty(cap, dtype=torch.int32, device=dev)
+        elen = torch.empty(cap, dtype=torch.float32, device=dev)
+        ne = torch.zeros(1, dtype=torch.int32, device=dev)
+        out = _lib.ForwardOut(_ptr(eg), _ptr(el), _ptr(erow), _ptr(ecol), _ptr(etyp), _ptr(elen), _ptr(ne))
+        fn = lib.agd_build_edges if build_only else lib.agd_forward
+        _lib.check(fn(self._native_handle(), nb.handle, _ptr(pos), C.byref(out), self._stream()))
+        E = int(ne.item())
+        if E > nb.cap:
+            raise RuntimeError("edge count %d exceeded the planned capacity %d" % (E, nb.cap))
+        edge_index = torch.stack([erow[:E].long(), ecol[:E].long()])
+        edge_type = etyp[:E].long()
+        edge_length = elen[:E].unsqueeze(-1)
+        if build_only:
+            return edge_index, edge_type, edge_length
+        return (eg[:E].unsqueeze(-1), el[:nb.n_local].unsqueeze(-1), edge_index, edge_type, edge_length, edge_type > 0)
+
+    def build_edges(self, pos, bond_index, bond_type, batch, extend_order=True):
+        """extend_graph_order_radius + get_distance (reference common.py:236-264, geometry.py:5-6)."""
+        self._sync_weights()
+        nb = self._prepare(torch.zeros_like(batch), bond_index, bond_type, batch, extend_order)
+        try:
+            return self._forward_native(nb, pos, build_only=True)
+        finally:
+            nb.close()
+
+    # ------------------------------------------------------------------ loss (out of scope)
+    def get_loss(self, *args, **kwargs):
+        raise NotImplementedError("training (get_loss / autograd) is outside the accelerated sampling path")
+
+    get_loss_diffusion = get_loss
+
+    # ------------------------------------------------------------------ samplers
+    def langevin_dynamics_sample(self, atom_type, pos_init, bond_index, bond_type, batch, num_graphs, extend_order,
+                                 extend_radius=True, n_steps=5000, step_lr=0.0000010, clip=1000, clip_local=None,
+                                 clip_pos=None, min_sigma=0, global_start_sigma=float("inf"), w_global=0.2, w_reg=1.0,
+                                 **kwargs):
+        """dispatcher, reference dualenc.py:397-439 (forwards sampling_type / eta, which are ignored)."""
+        return self.langevin_dynamics_sample_diffusion(
+            atom_type, pos_init, bond_index, bond_type, batch, num_graphs, extend_order, extend_radius, n_steps,
+            step_lr, clip, clip_local, clip_pos, min_sigma, global_start_sigma, w_global, w_reg, **kwargs)
+
+    def step_schedule(self, n_steps, step_lr, global_start_sigma, t_start=None):
+        """Per-step scalars in the reference's own fp32 tensor arithmetic (dualenc.py:468,515,532-533)."""
+        alphas = self.alphas.detach().to("cpu", torch.float32)
+        sigmas = (1.0 - alphas).sqrt() / alphas.sqrt()
+        T = self.num_timesteps if t_start is None else t_start
+        sig = np.zeros(n_steps, np.float32)
+        stp = np.zeros(n_steps, np.float32)
+        nsc = np.zeros(n_steps, np.float32)
+        glb = np.zeros(n_steps, np.uint8)
+        for s, i in enumerate(range(T - 1, T - n_steps - 1, -1)):
+            step_size = step_lr * (sigmas[i] / 0.01) ** 2
+            sig[s] = float(sigmas[i])
+            stp[s] = float(step_size)
+            nsc[s] = float(torch.sqrt(step_size * 2))
+            glb[s] = 1 if bool(sigmas[i] < global_start_sigma) else 0
+        return sigmas, sig, stp, nsc, glb
+
+    def langevin_dynamics_sample_diffusion(self, atom_type, pos_init, bond_index, bond_type, batch, num_graphs,
+                                           extend_order, extend_radius=True, n_steps=5000, step_lr=0.0000010, clip=1000,
+                                           clip_local=None, clip_pos=None, min_sigma=0, global_start_sigma=float("inf"),
+                                           w_global=0.2, w_reg=1.0, **kwargs):
+        """reference dualenc.py:441-547.  Returns (pos, pos_traj) with pos on the model's device and
+        pos_traj a list of n_steps CPU tensors (empty when return_traj=False)."""
+        if not extend_radius:
+            raise NotImplementedError("extend_radius=False is not on the native path")
+        noise = kwargs.get("noise")
+        seed = int(kwargs.get("seed", torch.initial_seed() & 0x7FFFFFFFFFFFFFFF))
+        return_traj = bool(kwargs.get("return_traj", True))
+        use_graph = bool(kwargs.get("use_cuda_graph", True))
+        t_start = kwargs.get("t_start")            # extension: run a window of the schedule
+        scale_init = bool(kwargs.get("scale_init", True))
+        window = int(kwargs.get("traj_window", 256))
+        lib, dev = _lib.load(), self._device()
+        self.eval()
+        atom_type = atom_type.to(dev)
+        self._renorm_embedding(atom_type)
+        self._sync_weights()
+        sigmas, sig, stp, nsc, glb = self.step_schedule(n_steps, step_lr, global_start_sigma, t_start)
+        with torch.no_grad():
+            pos = pos_init.to(dev, torch.float32)
+            pos = (pos * sigmas[-1].to(dev)) if scale_init else pos.clone()
+            pos = pos.contiguous()
+            N = pos.size(0)
+            if noise is not None:
+                noise = noise.to(dev, torch.float32).contiguous()
+                assert noise.shape == (n_steps, N, 3)
+            nb = self._prepare(atom_type, bond_index, bond_type, batch, extend_order, kwargs.get("mol_gid"))
+            traj_host = None
+            try:
+                if return_traj and n_steps > 0:
+                    traj_host = torch.empty((n_steps, N, 3), dtype=torch.float32, pin_memory=True)
+                    tbuf = torch.empty((min(window, n_steps), N, 3), dtype=torch.float32, device=dev)
+                    spans = [(s, min(s + window, n_steps)) for s in range(0, n_steps, window)]
+                else:
+                    tbuf = None
+                    spans = [(0, n_steps)] if n_steps > 0 else []
+                for s0, s1 in spans:
+                    p = _lib.SampleParams()
+                    p.n_steps = s1 - s0
+                    p.sigma = sig[s0:s1].ctypes.data_as(C.c_void_p)
+                    p.step_size = stp[s0:s1].ctypes.data_as(C.c_void_p)
+                    p.noise_scale = nsc[s0:s1].ctypes.data_as(C.c_void_p)
+                    p.use_global = glb[s0:s1].ctypes.data_as(C.c_void_p)
+                    p.w_global, p.clip = float(w_global), float(clip)
+                    p.clip_local = -1.0 if clip_local is None else float(clip_local)
+                    p.clip_pos = -1.0 if clip_pos is None else float(clip_pos)
+                    p.seed = seed
+                    p.step_offset = s0
+                    p.noise = _ptr(noise[s0:s1]) if noise is not None else None
+                    p.traj = _ptr(tbuf) if tbuf is not None else None
+                    p.use_cuda_graph = 1 if use_graph else 0
+                    nan_step = C.c_int32(-1)
+                    rc = lib.agd_sample(self._native_handle(), nb.handle, _ptr(pos), C.byref(p), C.byref(nan_step),
+                                        self._stream())
+                    if rc == _lib.AGD_ERR_NAN:
+                        print("NaN detected. Please restart.")
+                        raise FloatingPointError()
+                    _lib.check(rc)
+                    if tbuf is not None:
+                        traj_host[s0:s1].copy_(tbuf[: s1 - s0], non_blocking=True)
+                        torch.cuda.current_stream(dev).synchronize()
+            finally:
+                nb.close()
+        pos_traj: List[torch.Tensor] = list(traj_host.unbind(0)) if traj_host is not None else []
+        return pos, pos_traj
+
+
+def get_model(config):
+    """reference src/agdiff/models/epsnet/__init__.py:4-8"""
+    if config.network == "dualenc":
+        return DualEncoderEpsNetwork(config)
+    raise NotImplementedError("Unknown network: %s" % config.network)

@@ -1,0 +1,136 @@
+"""state_dict -> packed device weights.
+
+Done once per model (fp64 on the host), so that no per-edge FLOP is spent on it:
+  * BatchNorm1d in eval mode (running stats, eps=1e-5) is folded into the preceding Linear
+    (reference schnet.py:153-158, gin.py:131-132);
+  * every Linear is stored transposed ([K][N]) for the [K][N]-streaming tile GEMM;
+  * the bond-embedding halves of the edge encoder's two 256->128 Linears become per-type tables,
+    and edge_feature_mlp.2 -> combination_mlp.0 collapses into one 128x128 matrix (edge.py:84-101);
+  * on the global branch ``edge_attr`` is only consumed by Linears (CFConv filter nets
+    schnet.py:151, pair MLP common.py:106-109), so combination_mlp.2 is merged into those;
+  * the SchNet embedding table has its max_norm=10 renormalisation pre-applied (schnet.py:254).
+The attention branch of MLPEdgeEncoder multiplies by a softmax over a size-1 dimension (== 1.0),
+``edge_encoder_local`` and ``CFConv.attention`` are never evaluated by the reference forward
+(dualenc.py:214, schnet.py:126) -- none of them is packed.
+
+The slot list (names, sizes, order) is owned by the native library and queried at run time.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import numpy as np
+import torch
+
+BN_EPS = 1e-5
+
+
+def _f64(t: torch.Tensor) -> np.ndarray:
+    return t.detach().to("cpu", torch.float64).numpy()
+
+
+def _fold_bn(sd, lin_key, bn_key):
+    w, b = _f64(sd[lin_key + ".weight"]), _f64(sd[lin_key + ".bias"])
+    g, beta = _f64(sd[bn_key + ".weight"]), _f64(sd[bn_key + ".bias"])
+    mean, var = _f64(sd[bn_key + ".running_mean"]), _f64(sd[bn_key + ".running_var"])
+    s = g / np.sqrt(var + BN_EPS)
+    return (w * s[:, None]).T.copy(), (b - mean) * s + beta      # [K][N], [N]
+
+
+def fold_state_dict(sd: Dict[str, torch.Tensor], num_convs: int, num_convs_local: int) -> Dict[str, np.ndarray]:
+    """-> {slot name: float64 array}."""
+    out: Dict[str, np.ndarray] = {}
+    e = "edge_encoder_global."
+    bond = _f64(sd[e + "bond_emb.weight"])
+    L1, b1 = _f64(sd[e + "edge_feature_mlp.0.weight"]), _f64(sd[e + "edge_feature_mlp.0.bias"])
+    L2, b2 = _f64(sd[e + "edge_feature_mlp.2.weight"]), _f64(sd[e + "edge_feature_mlp.2.bias"])
+    C1, cb1 = _f64(sd[e + "combination_mlp.0.weight"]), _f64(sd[e + "combination_mlp.0.bias"])
+    C2, cb2 = _f64(sd[e + "combination_mlp.2.weight"]), _f64(sd[e + "combination_mlp.2.bias"])
+    H = L2.shape[0]
+    out["enc.fe_w"] = _f64(sd[e + "feature_expansion.weight"])[:, 0]
+    out["enc.fe_b"] = _f64(sd[e + "feature_expansion.bias"])
+    out["enc.W1"] = L1[:, :H].T
+    out["enc.T1"] = bond @ L1[:, H:].T + b1
+    out["enc.M2"] = (C1[:, :H] @ L2).T
+    out["enc.T2"] = bond @ C1[:, H:].T + (C1[:, :H] @ b2 + cb1)
+    out["enc.C2"] = C2.T
+    out["enc.c2b"] = cb2
+
+    g = "encoder_global."
+    emb = _f64(sd[g + "embedding.weight"]).copy()
+    nrm = np.linalg.norm(emb, axis=1, keepdims=True)
+    emb = np.where(nrm > 10.0, emb * (10.0 / (nrm + 1e-7)), emb)
+    out["sch.emb"] = emb
+    for k in range(num_convs):
+        ip = "%sinteractions.%d." % (g, k)
+        p = "blk%d." % k
+        for c, tag in ((1, "a"), (2, "b")):
+            cp = "%sconv%d." % (ip, c)
+            W, bb = _fold_bn(sd, cp + "lin1", cp + "norm1")
+            out[p + "L1" + tag], out[p + "l1%sb" % tag] = W, bb
+            w0, b0 = _f64(sd[cp + "nn.0.weight"]), _f64(sd[cp + "nn.0.bias"])
+            out[p + "F1" + tag] = (w0 @ C2).T
+            out[p + "f1%sb" % tag] = w0 @ cb2 + b0
+            out[p + "F2" + tag] = _f64(sd[cp + "nn.2.weight"]).T
+            out[p + "f2%sb" % tag] = _f64(sd[cp + "nn.2.bias"])
+            dw = np.zeros(128)
+            dw[0:32] = _f64(sd[cp + "distance_weighting.layer1.weight"])[:, 0]
+            dw[32:64] = _f64(sd[cp + "distance_weighting.layer1.bias"])
+            dw[64:96] = _f64(sd[cp + "distance_weighting.layer2.weight"])[0]
+            dw[96] = _f64(sd[cp + "distance_weighting.layer2.bias"])[0]
+            out[p + "dw%d" % c] = dw
+            W, bb = _fold_bn(sd, cp + "lin2", cp + "norm2")
+            out[p + "L2" + tag], out[p + "l2%sb" % tag] = W, bb
+        out[p + "LIN"] = _f64(sd[ip + "lin.weight"]).T
+        out[p + "linb"] = _f64(sd[ip + "lin.bias"])
+        out[p + "A1"] = _f64(sd[ip + "attention.0.weight"]).T
+        out[p + "a1b"] = _f64(sd[ip + "attention.0.bias"])
+        out[p + "a2w"] = _f64(sd[ip + "attention.2.weight"])[0]
+        sp = "%sscaling_modules.%d." % (g, k)
+        out[p + "S1"] = _f64(sd[sp + "fc.0.weight"]).T
+        out[p + "S2"] = _f64(sd[sp + "fc.2.weight"]).T
+        out[p + "sc"] = np.array([float(sd[ip + "conv1.nn.1.beta"]), float(sd[ip + "conv2.nn.1.beta"]),
+                                  float(sd[ip + "act.beta"]), float(_f64(sd[ip + "attention.2.bias"])[0])])
+
+    for pre, p, merged in (("grad_global_dist_mlp.", "pg.", True), ("grad_local_dist_mlp.", "pl.", False)):
+        W0, b0 = _f64(sd[pre + "layers.0.weight"]), _f64(sd[pre + "layers.0.bias"])
+        out[p + "P1h"] = W0[:, :H].T
+        if merged:
+            out[p + "P1e"] = (W0[:, H:] @ C2).T
+            out[p + "p1b"] = b0 + W0[:, H:] @ cb2
+        else:
+            out[p + "P1e"] = W0[:, H:].T
+            out[p + "p1b"] = b0
+        out[p + "P2"] = _f64(sd[pre + "layers.1.weight"]).T
+        out[p + "p2b"] = _f64(sd[pre + "layers.1.bias"])
+        out[p + "p3w"] = _f64(sd[pre + "layers.2.weight"])[0]
+        out[p + "p3b"] = _f64(sd[pre + "layers.2.bias"])
+
+    l = "encoder_local."
+    out["gin.emb"] = _f64(sd[l + "node_emb.weight"])
+    for k in range(num_convs_local):
+        p = "gin%d." % k
+        out[p + "G1"] = _f64(sd["%sconvs.%d.nn.layers.0.weight" % (l, k)]).T
+        out[p + "g1b"] = _f64(sd["%sconvs.%d.nn.layers.0.bias" % (l, k)])
+        W, bb = _fold_bn(sd, "%sconvs.%d.nn.layers.1" % (l, k), "%sbatch_norms.%d" % (l, k))
+        out[p + "G2"], out[p + "g2b"] = W, bb
+        out[p + "sc"] = np.array([1.0 + float(_f64(sd["%sconvs.%d.eps" % (l, k)])[0])])
+    return out
+
+
+def pack(folded: Dict[str, np.ndarray], slot_names, slot_sizes, align: int = 32):
+    """Lay the folded arrays out in the library's slot order -> (float32 buffer, int64 offsets)."""
+    offsets = []
+    total = 0
+    for name, size in zip(slot_names, slot_sizes):
+        if name not in folded:
+            raise KeyError("packer has no tensor for native weight slot %r" % name)
+        arr = folded[name]
+        if arr.size != size:
+            raise ValueError("slot %s: expected %d floats, packer produced %d" % (name, size, arr.size))
+        offsets.append(total)
+        total += (size + align - 1) // align * align
+    buf = np.zeros(total, dtype=np.float32)
+    for name, size, off in zip(slot_names, slot_sizes, offsets):
+        buf[off:off + size] = np.ascontiguousarray(folded[name], dtype=np.float64).reshape(-1).astype(np.float32)
+    return buf, np.asarray(offsets, dtype=np.int64)

@@ -1,0 +1,169 @@
+/* agdiff_b200 -- C ABI of the B200-native AGDIFF sampling hot path.
+ *
+ * The reference (ADicksonLab/AGDIFF) has NO plugin/FFI layer: its boundary for this path is the
+ * Python class DualEncoderEpsNetwork (src/agdiff/models/epsnet/dualenc.py:54).  These entry points
+ * are what a maintainer would bind from that class (ctypes stub shown in INTEGRATION.md); each one
+ * cites the reference code it replaces.  Conventions: plain C, int return codes (0 = ok, <0 =
+ * error, text via agd_last_error()), no C++ exceptions cross the boundary, every pointer marked
+ * "dev" is a CUDA device pointer on the handle's device, "host" is host memory, all launches go
+ * to the caller-supplied cudaStream_t (passed as void*), one handle per device, a handle is not
+ * thread-safe.  There is no CPU fallback: every call fails with AGD_ERR_CUDA without a GPU.
+ */
+#ifndef AGDIFF_B200_H
+#define AGDIFF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGD_ABI_VERSION 1
+#define AGD_HIDDEN 128            /* hidden_dim; pinned by Linear(256, hidden) at schnet.py:190-192 */
+#define AGD_MAX_MOL_ATOMS 256     /* per-molecule limit of the adjacency bit-matrix edge builder    */
+#define AGD_MAX_RADIUS_NBRS 32    /* torch_cluster default used by common.py:217                    */
+
+enum {
+  AGD_OK = 0,
+  AGD_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+  AGD_ERR_CUDA = -2,      /* CUDA runtime error (text in agd_last_error) */
+  AGD_ERR_CAPACITY = -3,  /* a caller-supplied buffer or the workspace is too small */
+  AGD_ERR_NAN = -4        /* NaN positions during sampling (FloatingPointError, dualenc.py:539-541) */
+};
+
+typedef struct agd_handle agd_handle;   /* model: configuration + packed device weights */
+typedef struct agd_batch agd_batch;     /* one batch of molecules: topology + workspace  */
+
+/* configs/{qm9,drugs}_default.yml "model:" block, fields read at dualenc.py:64-98,173-174 */
+typedef struct {
+  int32_t hidden_dim;        /* must be 128 */
+  int32_t num_convs;         /* SchNet interaction blocks (6) */
+  int32_t num_convs_local;   /* GIN layers (4) */
+  int32_t smooth_conv;       /* 0: gaussian cutoff, 1: cosine cutoff (schnet.py:140-145) */
+  float cutoff;              /* 10.0 */
+  int32_t device;            /* CUDA device ordinal */
+} agd_config;
+
+/* Topology of a batch, int32, device pointers; built once per sampler call by the host mirror.
+ * "static" edges = the caller's bond graph after bond-order extension (common.py:135-205 /
+ * transforms.py:44-71), coalesced (sorted by row*N+col, duplicate types summed).  They are given
+ * twice: in CSC order (grouped by destination = edge_index[1], sources ascending) and by their
+ * position in canonical order.  "local" edges are the static edges with type > 0
+ * (dualenc.py:566-567); when every static type is > 0 both lists coincide. */
+typedef struct {
+  int32_t n_atoms, n_mols;
+  const int32_t* atom_type;   /* dev [n_atoms]   atomic numbers, < 100 */
+  const int32_t* mol_ptr;     /* dev [n_mols+1]  atoms of molecule m = mol_ptr[m] .. mol_ptr[m+1) */
+  const int32_t* atom_mol;    /* dev [n_atoms]   molecule of each atom (the sorted `batch` vector) */
+  const int64_t* mol_gid;     /* dev [n_mols]    global molecule id (keys the Philox noise stream) */
+  /* static edges, CSC order */
+  int32_t n_static;
+  const int32_t* st_src;      /* dev [n_static] edge_index[0] */
+  const int32_t* st_dst;      /* dev [n_static] edge_index[1] */
+  const int32_t* st_type;     /* dev [n_static] */
+  const int32_t* st_in_ptr;   /* dev [n_atoms+1] */
+  /* local edges (type > 0), CSC order + canonical bookkeeping */
+  int32_t n_local;
+  const int32_t* lc_src;      /* dev [n_local] */
+  const int32_t* lc_dst;      /* dev [n_local] */
+  const int32_t* lc_type;     /* dev [n_local] */
+  const int32_t* lc_in_ptr;   /* dev [n_atoms+1] */
+  const int32_t* lc_canon;    /* dev [n_local] position of CSC edge e in canonical (row-major) order */
+  const int32_t* lc_out_ptr;  /* dev [n_atoms+1] canonical segments by source atom */
+  const int32_t* lc_cdst;     /* dev [n_local] destination atom of canonical local edge */
+  int64_t edge_capacity;      /* upper bound on edges after radius extension for this batch */
+} agd_batch_desc;
+
+/* langevin_dynamics_sample_diffusion arguments (dualenc.py:441-461).  Per-step scalars are
+ * computed by the host mirror in fp32 exactly as dualenc.py:468,515,532-533 do. */
+typedef struct {
+  int32_t n_steps;
+  const float* sigma;        /* host [n_steps] sigmas[i], i = T-1 ... T-n_steps            */
+  const float* step_size;    /* host [n_steps] step_lr * (sigma/0.01)^2                    */
+  const float* noise_scale;  /* host [n_steps] sqrt(2*step_size)                           */
+  const uint8_t* use_global; /* host [n_steps] sigma < global_start_sigma (dualenc.py:515) */
+  float w_global;
+  float clip;                /* global clip_norm limit (dualenc.py:523) */
+  float clip_local;          /* < 0: no local clipping (clip_local=None) */
+  float clip_pos;            /* < 0: no clamp (clip_pos=None) */
+  uint64_t seed;             /* Philox seed when noise == NULL */
+  const float* noise;        /* dev [n_steps][n_atoms][3] injected noise, or NULL */
+  float* traj;               /* dev [n_steps][n_atoms][3] positions after each step, or NULL */
+  int32_t use_cuda_graph;    /* 1: replay captured per-step graphs, 0: plain launches */
+  int32_t step_offset;       /* index of this call's first step within the whole trajectory (Philox counter) */
+} agd_sample_params;
+
+/* forward outputs (dualenc.py:241-251), caller-allocated device buffers sized edge_capacity /
+ * n_local; canonical (row-major sorted) edge order, int32 indices (the host mirror widens to
+ * int64).  Any pointer may be NULL to skip that output. */
+typedef struct {
+  float* edge_inv_global;   /* dev [cap]      */
+  float* edge_inv_local;    /* dev [n_local]  canonical order of the local edges */
+  int32_t* edge_row;        /* dev [cap] edge_index[0] */
+  int32_t* edge_col;        /* dev [cap] edge_index[1] */
+  int32_t* edge_type;       /* dev [cap] */
+  float* edge_length;       /* dev [cap] */
+  int32_t* n_edges;         /* dev [1]   */
+} agd_forward_out;
+
+int agd_abi_version(void);
+const char* agd_last_error(void);
+
+/* get_model(config) (epsnet/__init__.py:4-8) + .to(device) */
+int agd_create(const agd_config* cfg, agd_handle** out);
+void agd_destroy(agd_handle* h);
+
+/* The packed-weight layout is owned by the library: slot i has a name and a float count; the host
+ * mirror folds BatchNorm(eval), merges back-to-back Linears and transposes in fp64, then uploads.
+ * Replaces load_state_dict + eval() for this path (scripts/test.py:111-114). */
+int agd_weight_slot_count(const agd_handle* h);
+const char* agd_weight_slot_name(const agd_handle* h, int slot);
+int64_t agd_weight_slot_size(const agd_handle* h, int slot);
+int agd_load_weights(agd_handle* h, const float* packed_host, const int64_t* slot_offsets, int n_slots,
+                     int64_t n_floats);
+
+/* workspace is owned by the library (cudaMalloc); size query for planning */
+int64_t agd_batch_workspace_bytes(const agd_handle* h, const agd_batch_desc* d);
+int agd_batch_create(agd_handle* h, const agd_batch_desc* d, agd_batch** out);
+void agd_batch_destroy(agd_batch* b);
+
+/* extend_graph_order_radius + get_distance (common.py:236-264, geometry.py:5-6): builds the
+ * canonical edge list for `pos`; outputs as in agd_forward_out (edge_inv_* ignored). */
+int agd_build_edges(agd_handle* h, agd_batch* b, const float* pos_dev, const agd_forward_out* out, void* stream);
+
+/* DualEncoderEpsNetwork.forward(..., return_edges=True, extend_radius=True) (dualenc.py:142-251)
+ * for a batch whose static edges are already order-extended. */
+int agd_forward(agd_handle* h, agd_batch* b, const float* pos_dev, const agd_forward_out* out, void* stream);
+
+/* langevin_dynamics_sample_diffusion loop body x n_steps (dualenc.py:476-545), in place on pos.
+ * first_nan_step (host, may be NULL) receives the first step whose update produced NaN or -1;
+ * the call returns AGD_ERR_NAN in that case (the host mirror raises FloatingPointError). */
+int agd_sample(agd_handle* h, agd_batch* b, float* pos_dev_inout, const agd_sample_params* p,
+               int32_t* first_nan_step, void* stream);
+
+/* _extend_graph_order / AddHigherOrderEdges (common.py:135-205) on device for one batch:
+ * CSR bond graph in, per-atom sorted (dst, type) lists out; two passes (count, fill). */
+int agd_extend_bond_order(const int32_t* mol_ptr, int32_t n_mols, int32_t n_atoms, const int32_t* bond_ptr,
+                          const int32_t* bond_dst, const int32_t* bond_type, int32_t order, int32_t num_bond_types,
+                          int32_t* out_count /* dev [n_atoms] */, const int32_t* out_ptr /* dev [n_atoms+1] or NULL */,
+                          int32_t* out_dst, int32_t* out_type, void* stream);
+
+/* stand-alone kernels exported for the roofline microbenchmarks (BASELINE.json config 4) and for
+ * module-level parity tests; all operate on CSC-sorted edges. */
+int agd_op_cfconv_aggregate(const float* x /*dev [N][F]*/, const float* W /*dev [E][F]*/, const int32_t* src,
+                            const int32_t* in_ptr, int32_t n_nodes, int32_t F, float* out /*dev [N][F]*/, void* stream);
+int agd_op_eq_transform(const float* score /*dev [E]*/, const float* pos, const int32_t* src, const int32_t* dst,
+                        const float* length, int64_t n_edges, int32_t n_nodes, float* out /*dev [N][3]*/, void* stream);
+
+/* debugging / tests: copy an internal per-batch tensor to a caller device buffer.  Names:
+ * "g2", "h_global", "h_local", "ea_local", "xcat", "agg", "filt".  Returns element count or <0. */
+int64_t agd_debug_fetch(agd_batch* b, const char* name, float* dst_dev, int64_t capacity);
+
+/* number of kernel launches issued by the library since the handle was created */
+int64_t agd_launch_count(const agd_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGDIFF_B200_H */
