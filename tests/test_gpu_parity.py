@@ -1,0 +1,337 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle and against golden
+vectors produced by the unmodified reference.  Bars: bit-exact for edge lists; fp32 forward outputs
+within rtol 1e-4 (+ atol 1e-5 * max|ref|); 100-step trajectories under identical injected noise
+within 1e-3 Angstrom RMSD per molecule (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from agdiff_b200 import graph, synth
+from oracle import agdiff_oracle as O
+from util import CONFIGS, assert_close, checksum, golden, kabsch_free_rmsd, make_model, rel_err, state_dict_cpu
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+FWD = ["fwd_alanine2_qm9", "fwd_alanine2_far_qm9", "fwd_qm9x6_perturbed", "fwd_drugs_mixed_smooth_perturbed",
+       "fwd_drugs_mixed_far_smooth"]
+
+
+def _cuda_model(cfg_name, seed=2021, perturb=0, **cfg_over):
+    if cfg_over:
+        import agdiff_b200
+        from types import SimpleNamespace
+        torch.manual_seed(seed)
+        m = agdiff_b200.get_model(SimpleNamespace(**dict(CONFIGS[cfg_name], **cfg_over))).eval()
+        if perturb:
+            m.load_state_dict(O.perturb_state_dict(m.state_dict(), seed=perturb), strict=False)
+    else:
+        m = make_model(cfg_name, seed, perturb)
+    sd = state_dict_cpu(m)
+    return m.to(DEV), sd
+
+
+def _batch(kind, seed=0, scale=2.5, repeats=1):
+    if kind == "alanine":
+        mols = [graph.extend_bond_order_host(synth.alanine_dipeptide())]
+    elif kind == "qm9":
+        mols = [graph.extend_bond_order_host(m) for m in synth.qm9_like(24, seed=seed + 1)]
+    elif kind == "drugs":
+        mols = [graph.extend_bond_order_host(m) for m in synth.drugs_like(9, seed=seed + 2, force_max=True)]
+    z, bi, bt, b, G = graph.collate(mols, repeats)
+    pos = torch.randn(z.numel(), 3, generator=torch.Generator().manual_seed(seed + 3)) * scale
+    return z, bi, bt, b, G, pos
+
+
+def _stage_report(m, sd, cfg, z, pos, bi, bt, b):
+    """error table of intermediate tensors, used in assertion messages to localise a failure"""
+    col = {}
+    with torch.no_grad():
+        O.forward(sd, cfg, z, pos, bi, bt, b, extend_order=False, collect=col)
+    nb = m._prepare(z.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), False)
+    lines = []
+    try:
+        res = m._forward_native(nb, pos.to(DEV))
+        N = z.numel()
+        lines.append("h_global %.2e" % rel_err(nb.fetch("h_global", N * 128).view(N, 128), col["node_global"]))
+        lines.append("h_local %.2e" % rel_err(nb.fetch("h_local", N * 128).view(N, 128), col["node_local"]))
+        ei, et = res[2].cpu(), res[3].cpu()
+        lmask = et > 0
+        ea_ref = col["edge_attr"][lmask]
+        lperm = nb.lc_canon.long().cpu()
+        ea = nb.fetch("ea_local", max(nb.n_local, 1) * 128).view(-1, 128).cpu()
+        lines.append("ea_local %.2e" % rel_err(ea, ea_ref[lperm]))
+    finally:
+        nb.close()
+    return "; ".join(lines)
+
+
+# ------------------------------------------------------------------------------- edges
+@pytest.mark.parametrize("kind,scale", [("alanine", 3.0), ("alanine", 9.0), ("qm9", 2.0), ("drugs", 2.5), ("drugs", 6.0),
+                                        ("drugs", 0.5)])
+def test_edges_bit_exact(kind, scale):
+    m, sd = _cuda_model("qm9")
+    z, bi, bt, b, G, pos = _batch(kind, seed=5, scale=scale, repeats=2)
+    ei_ref, et_ref = O.build_edges(pos, bi, bt, b, CONFIGS["qm9"], extend_order=False)
+    len_ref = O.edge_lengths(pos, ei_ref)
+    ei, et, elen = m.build_edges(pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), extend_order=False)
+    assert ei.dtype == torch.long and et.dtype == torch.long
+    assert ei.shape == ei_ref.shape, "edge count %s vs %s" % (tuple(ei.shape), tuple(ei_ref.shape))
+    assert torch.equal(ei.cpu(), ei_ref) and torch.equal(et.cpu(), et_ref)
+    assert_close(elen.view(-1), len_ref, rtol=1e-6, atol_scale=1e-7, what="edge_length")
+
+
+def test_edges_exactly_at_cutoff():
+    """atoms exactly at / just inside / just outside the cutoff and the 33-neighbour truncation"""
+    m, sd = _cuda_model("qm9")
+    n = 40
+    mol = synth._random_molecule(np.random.default_rng(0), n, 22, (6, 7, 8), 2)
+    mol = graph.extend_bond_order_host(mol)
+    z, bi, bt, b, G = graph.collate([mol], 1)
+    pos = torch.zeros(n, 3)
+    pos[:, 0] = torch.arange(n, dtype=torch.float32) * 0.25          # a line: everyone within 10 A -> truncation
+    pos[-1] = torch.tensor([10.0, 0.0, 0.0])                          # exactly 10.0 from atom 0: strict '<' excludes
+    pos[-2] = torch.tensor([np.nextafter(np.float32(10.0), np.float32(0.0)), 0.0, 0.0])
+    ei_ref, et_ref = O.build_edges(pos, bi, bt, b, CONFIGS["qm9"], extend_order=False)
+    ei, et, _ = m.build_edges(pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), extend_order=False)
+    assert torch.equal(ei.cpu(), ei_ref) and torch.equal(et.cpu(), et_ref)
+
+
+def test_bond_order_extension_device():
+    g = golden("bond_order_ext")
+    m, sd = _cuda_model("qm9")
+    N = g["atom_type"].numel()
+    row, col, typ = m._static_edges(N, g["bond_index"].to(DEV), g["bond_type"].to(DEV), g["batch"].to(DEV), True)
+    assert torch.equal(torch.stack([row, col]).cpu(), g["ext_index"]) and torch.equal(typ.cpu(), g["ext_type"])
+
+
+# ------------------------------------------------------------------------------- forward
+@pytest.mark.parametrize("name", FWD)
+def test_forward_matches_reference_golden(name):
+    g = golden(name)
+    m, sd = _cuda_model(g["cfg_name"], g["seed"], g["perturb"])
+    assert abs(checksum(sd) - g["checksum"]) <= 1e-9 * g["checksum"]
+    eg, el, ei, et, elen, mask = m(g["atom_type"].to(DEV), g["pos"].to(DEV), g["bond_index"].to(DEV),
+                                   g["bond_type"].to(DEV), g["batch"].to(DEV), None, return_edges=True,
+                                   extend_order=False)
+    assert torch.equal(ei.cpu(), g["edge_index"]) and torch.equal(et.cpu(), g["edge_type"])
+    assert torch.equal(mask.cpu(), g["edge_type"] > 0)
+    assert eg.shape == g["edge_inv_global"].shape and el.shape == g["edge_inv_local"].shape
+    try:
+        assert_close(elen, g["edge_length"], rtol=1e-6, atol_scale=1e-7, what="edge_length")
+        assert_close(el, g["edge_inv_local"], what="edge_inv_local")
+        assert_close(eg, g["edge_inv_global"], what="edge_inv_global")
+    except AssertionError as e:
+        rep = _stage_report(m, sd, CONFIGS[g["cfg_name"]], g["atom_type"], g["pos"], g["bond_index"], g["bond_type"],
+                            g["batch"])
+        raise AssertionError(str(e) + " | stages: " + rep)
+
+
+@pytest.mark.parametrize("cfg_name,kind,scale,perturb", [("qm9", "qm9", 2.0, 3), ("drugs", "drugs", 2.5, 4),
+                                                         ("drugs", "drugs", 7.0, 0), ("qm9", "drugs", 1.0, 5)])
+def test_forward_matches_oracle(cfg_name, kind, scale, perturb):
+    m, sd = _cuda_model(cfg_name, 2021, perturb)
+    z, bi, bt, b, G, pos = _batch(kind, seed=21, scale=scale, repeats=2)
+    with torch.no_grad():
+        ref = O.forward(sd, CONFIGS[cfg_name], z, pos, bi, bt, b, extend_order=False)
+    out = m(z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), None, return_edges=True, extend_order=False)
+    assert torch.equal(out[2].cpu(), ref[2]) and torch.equal(out[3].cpu(), ref[3])
+    try:
+        assert_close(out[1], ref[1], what="edge_inv_local")
+        assert_close(out[0], ref[0], what="edge_inv_global")
+    except AssertionError as e:
+        raise AssertionError(str(e) + " | stages: " + _stage_report(m, sd, CONFIGS[cfg_name], z, pos, bi, bt, b))
+
+
+@pytest.mark.parametrize("num_convs,num_convs_local", [(1, 1), (2, 3)])
+def test_forward_reduced_depth(num_convs, num_convs_local):
+    """shallower configs localise a failing block (config fields are honoured, not hard-coded)"""
+    m, sd = _cuda_model("drugs", 2021, 6, num_convs=num_convs, num_convs_local=num_convs_local)
+    cfg = dict(CONFIGS["drugs"], num_convs=num_convs, num_convs_local=num_convs_local)
+    z, bi, bt, b, G, pos = _batch("qm9", seed=2, scale=2.0)
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, z, pos, bi, bt, b, extend_order=False)
+    out = m(z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), None, return_edges=True, extend_order=False)
+    try:
+        assert_close(out[1], ref[1], what="edge_inv_local")
+        assert_close(out[0], ref[0], what="edge_inv_global")
+    except AssertionError as e:
+        raise AssertionError(str(e) + " | stages: " + _stage_report(m, sd, cfg, z, pos, bi, bt, b))
+
+
+def test_forward_extend_order_default():
+    """forward's default extend_order=True: bond graph in, 2-/3-hop edges added on device"""
+    m, sd = _cuda_model("qm9", 2021, 2)
+    mols = synth.qm9_like(5, seed=9) + [synth.alanine_dipeptide()]
+    z, bi, bt, b, G = graph.collate(mols, 1)
+    pos = torch.randn(z.numel(), 3, generator=torch.Generator().manual_seed(4)) * 2.0
+    with torch.no_grad():
+        ref = O.forward(sd, CONFIGS["qm9"], z, pos, bi, bt, b, extend_order=True)
+    out = m(z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), None, return_edges=True)
+    assert torch.equal(out[2].cpu(), ref[2]) and torch.equal(out[3].cpu(), ref[3])
+    assert_close(out[0], ref[0], what="edge_inv_global")
+    assert_close(out[1], ref[1], what="edge_inv_local")
+    eg2, el2 = m(z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), None)      # return_edges=False form
+    assert torch.equal(eg2, out[0]) and torch.equal(el2, out[1])
+
+
+def test_state_dict_roundtrip_and_renorm_side_effect():
+    m, sd = _cuda_model("qm9", 2021, 8)
+    m2, _ = _cuda_model("qm9", 1, 0)
+    m2.load_state_dict(sd)                      # 854 keys incl. model_global/model_local aliases
+    z, bi, bt, b, G, pos = _batch("alanine", seed=1, scale=3.0, repeats=2)
+    args = (z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), None)
+    a = m(*args, extend_order=False)
+    c = m2(*args, extend_order=False)
+    assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+    w = m.encoder_global.embedding.weight
+    used = torch.unique(z)
+    assert float(w[used.to(DEV)].norm(dim=1).max()) <= 10.0 + 1e-4      # accessed rows renormed in place (schnet.py:254)
+    assert len(m.state_dict()) == 854
+
+
+# ------------------------------------------------------------------------------- sampler
+@pytest.mark.parametrize("name", ["traj_alanine2_high", "traj_alanine2_low", "traj_qm9x6_low_smooth"])
+def test_trajectory_matches_reference_golden(name):
+    g = golden(name)
+    m, sd = _cuda_model(g["cfg_name"], g["seed"], 0)
+    n_steps = g["n_steps"]
+    noise = torch.randn(n_steps, g["atom_type"].numel(), 3, generator=torch.Generator().manual_seed(g["noise_seed"]))
+    G = int(g["batch"].max()) + 1
+    kw = dict(extend_order=False, n_steps=n_steps, step_lr=1e-6, clip=1000.0, clip_local=g["clip_local"],
+              global_start_sigma=g["global_start_sigma"], w_global=g["w_global"], noise=noise, t_start=g["t_start"],
+              scale_init=g["scale_init"])
+    pos, traj = m.langevin_dynamics_sample_diffusion(g["atom_type"].to(DEV), g["pos_init"].to(DEV), g["bond_index"].to(DEV),
+                                                     g["bond_type"].to(DEV), g["batch"].to(DEV), G, **kw)
+    assert len(traj) == n_steps and traj[0].device.type == "cpu" and pos.device.type == "cuda"
+    assert torch.equal(traj[-1], pos.cpu())
+    for k, ref in zip(g["traj_steps"].tolist(), g["traj"]):
+        r = kabsch_free_rmsd(traj[k], ref, g["batch"])
+        assert float(r.max()) <= 1e-3, "step %d: RMSD %.3e A" % (k, float(r.max()))
+    r = kabsch_free_rmsd(pos, g["pos_final"], g["batch"])
+    assert float(r.max()) <= 1e-3, "final RMSD %.3e A" % float(r.max())
+    # plain launches and graph replay are the same arithmetic
+    pos2, _ = m.langevin_dynamics_sample_diffusion(g["atom_type"].to(DEV), g["pos_init"].to(DEV), g["bond_index"].to(DEV),
+                                                   g["bond_type"].to(DEV), g["batch"].to(DEV), G, use_cuda_graph=False,
+                                                   return_traj=False, **kw)
+    assert torch.equal(pos, pos2)
+
+
+def test_trajectory_drugs_vs_oracle():
+    """Drugs-shaped batch (incl. the 181-atom molecule), 30 steps across the global-start boundary"""
+    m, sd = _cuda_model("drugs", 2021, 0)
+    mols = [graph.extend_bond_order_host(x) for x in synth.drugs_like(5, seed=3, force_max=True)]
+    z, bi, bt, b, G = graph.collate(mols, 1)
+    n_steps, t_start = 30, 2027                  # sigma crosses 0.5 at i = 2012
+    gen = torch.Generator().manual_seed(8)
+    pos0 = O.center_pos(torch.randn(z.numel(), 3, generator=gen) * 1.5, b)
+    noise = torch.randn(n_steps, z.numel(), 3, generator=gen)
+    kw = dict(extend_order=False, n_steps=n_steps, step_lr=1e-6, clip=1000.0, clip_local=20.0, global_start_sigma=0.5,
+              w_global=1.0, noise=noise, t_start=t_start, scale_init=False)
+    with torch.no_grad():
+        ref, _ = O.sample(sd, CONFIGS["drugs"], z, pos0, bi, bt, b, G, keep_traj=False, **kw)
+    pos, traj = m.langevin_dynamics_sample_diffusion(z.to(DEV), pos0.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), G, **kw)
+    r = kabsch_free_rmsd(pos, ref, b)
+    assert float(r.max()) <= 1e-3, "RMSD %.3e A" % float(r.max())
+
+
+def test_sampler_properties():
+    m, sd = _cuda_model("qm9", 2021, 0)
+    z, bi, bt, b, G, pos = _batch("qm9", seed=6, scale=1.0)
+    args = (z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), G)
+    kw = dict(extend_order=False, n_steps=20, step_lr=1e-6, clip=1000.0, clip_local=20.0, global_start_sigma=0.5,
+              w_global=1.0, return_traj=False)
+    p1, t1 = m.langevin_dynamics_sample(*args, seed=11, **kw)       # dispatcher, reference dualenc.py:397
+    p2, _ = m.langevin_dynamics_sample_diffusion(*args, seed=11, **kw)
+    p3, _ = m.langevin_dynamics_sample_diffusion(*args, seed=12, **kw)
+    assert t1 == [] and torch.equal(p1, p2) and not torch.equal(p1, p3)      # deterministic in the seed
+    cen = torch.zeros(G, 3, device=DEV).index_add_(0, b.to(DEV), p1) / torch.bincount(b).to(DEV)[:, None]
+    assert float(cen.abs().max()) < 1e-3                                          # center_pos ran last
+    # sharding invariance: two halves with global molecule ids == the full batch
+    half = G // 2
+    cut = int((b < half).sum())
+    ecut = int((bi[0] < cut).sum())
+    gid = torch.arange(G)
+    pa, _ = m.langevin_dynamics_sample_diffusion(z[:cut].to(DEV), pos[:cut].to(DEV), bi[:, :ecut].to(DEV), bt[:ecut].to(DEV),
+                                                 b[:cut].to(DEV), half, seed=11, mol_gid=gid[:half], **kw)
+    pb, _ = m.langevin_dynamics_sample_diffusion(z[cut:].to(DEV), pos[cut:].to(DEV), (bi[:, ecut:] - cut).to(DEV),
+                                                 bt[ecut:].to(DEV), (b[cut:] - half).to(DEV), G - half, seed=11,
+                                                 mol_gid=gid[half:], **kw)
+    assert torch.equal(torch.cat([pa, pb]), p1)
+
+
+def test_device_noise_statistics():
+    """with zero drift weightings the update is pos + noise*sqrt(2*step): check N(0,1) moments"""
+    m, sd = _cuda_model("qm9", 2021, 0)
+    mols = [graph.extend_bond_order_host(x) for x in synth.qm9_like(400, seed=1)]
+    z, bi, bt, b, G = graph.collate(mols, 1)
+    pos0 = torch.zeros(z.numel(), 3)
+    pos0[:, 0] = torch.arange(z.numel()) % 7 * 0.01 + 0.01     # distinct positions (non-zero lengths)
+    pos, _ = m.langevin_dynamics_sample_diffusion(z.to(DEV), pos0.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), G,
+                                                  extend_order=False, n_steps=1, step_lr=1e-6, clip=1000.0,
+                                                  clip_local=0.0, global_start_sigma=0.0, w_global=0.0, seed=5,
+                                                  return_traj=False, scale_init=False)
+    _, sig, stp, nsc, _ = m.step_schedule(1, 1e-6, 0.0)
+    zed = ((pos.cpu() - O.center_pos(pos0, b)) / float(nsc[0]))
+    # centering removes 1/n of the variance per molecule; compare against that
+    n_per = torch.bincount(b).float()[b]
+    expect_var = float((1 - 1 / n_per).mean())
+    assert abs(float(zed.mean())) < 0.02
+    assert abs(float(zed.var()) - expect_var) < 0.03
+    assert abs(float((zed ** 4).mean()) / float(zed.var()) ** 2 - 3.0) < 0.25
+
+
+def test_nan_raises_floating_point_error():
+    """random-init weights without clip_local diverge within a few steps; the
+    reference raises FloatingPointError (dualenc.py:539-541) and callers rely on it."""
+    m, sd = _cuda_model("qm9", 2021, 0)
+    z, bi, bt, b, G, pos = _batch("alanine", seed=1, scale=1.0, repeats=2)
+    with pytest.raises(FloatingPointError):
+        m.langevin_dynamics_sample_diffusion(z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), G,
+                                             extend_order=False, n_steps=60, step_lr=1e-6, clip=1000.0, clip_local=None,
+                                             global_start_sigma=0.5, w_global=1.0, seed=3)
+
+
+# ------------------------------------------------------------------------------- stand-alone ops
+@pytest.mark.parametrize("F", [64, 128, 192])
+def test_op_cfconv_aggregate(F):
+    import ctypes as C
+    from agdiff_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(0)
+    N, deg = 1000, 17
+    E = N * deg
+    dst = torch.arange(N).repeat_interleave(deg)
+    src = torch.randint(0, N, (E,), generator=gen)
+    x = torch.rand(N, F, generator=gen) * 2 - 1
+    W = torch.rand(E, F, generator=gen) * 2 - 1
+    ref = torch.zeros(N, F, dtype=torch.float64).index_add_(0, dst, (x[src] * W).double())
+    in_ptr = torch.arange(N + 1, dtype=torch.int32) * deg
+    xd, Wd, sd_, pd = x.to(DEV), W.to(DEV), src.to(torch.int32).to(DEV), in_ptr.to(DEV)
+    out = torch.empty(N, F, device=DEV)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.agd_op_cfconv_aggregate(C.c_void_p(xd.data_ptr()), C.c_void_p(Wd.data_ptr()), C.c_void_p(sd_.data_ptr()),
+                                           C.c_void_p(pd.data_ptr()), N, F, C.c_void_p(out.data_ptr()), st))
+    torch.cuda.synchronize()
+    assert_close(out, ref, rtol=1e-5, atol_scale=1e-6, what="aggregate")
+
+
+def test_op_eq_transform():
+    import ctypes as C
+    from agdiff_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(1)
+    N, E = 500, 9000
+    pos = torch.randn(N, 3, generator=gen) * 3
+    ei = torch.randint(0, N, (2, E), generator=gen)
+    ei = ei[:, ei[0] != ei[1]]
+    E = ei.size(1)
+    s = torch.randn(E, 1, generator=gen)
+    ln = O.edge_lengths(pos, ei).unsqueeze(-1)
+    ref = O.eq_transform(s.double(), pos.double(), ei, ln.double())
+    out = torch.empty(N, 3, device=DEV)
+    a = [t.to(DEV).contiguous() for t in (s.view(-1), pos, ei[0].to(torch.int32), ei[1].to(torch.int32), ln.view(-1))]
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.agd_op_eq_transform(*[C.c_void_p(t.data_ptr()) for t in a], E, N, C.c_void_p(out.data_ptr()), st))
+    torch.cuda.synchronize()
+    assert_close(out, ref, rtol=1e-4, atol_scale=1e-5, what="eq_transform")
