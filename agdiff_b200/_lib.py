@@ -21,7 +21,7 @@ EXPORTS = [
     "agd_weight_slot_name", "agd_weight_slot_size", "agd_load_weights", "agd_batch_workspace_bytes",
     "agd_batch_create", "agd_batch_destroy", "agd_build_edges", "agd_forward", "agd_sample",
     "agd_extend_bond_order", "agd_op_cfconv_aggregate", "agd_op_eq_transform", "agd_debug_fetch",
-    "agd_launch_count",
+    "agd_launch_count", "agd_profile_forward",
 ]
 
 
@@ -97,6 +97,7 @@ def load() -> C.CDLL:
     lib.agd_op_eq_transform.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp]
     lib.agd_debug_fetch.argtypes = [vp, C.c_char_p, vp, i64]
     lib.agd_debug_fetch.restype = i64
+    lib.agd_profile_forward.argtypes = [vp, vp, vp, i32, C.c_char_p, i64, vp, i32, C.POINTER(i32), C.POINTER(i32), vp]
     lib.agd_launch_count.argtypes = [vp]
     lib.agd_launch_count.restype = i64
     if lib.agd_abi_version() != 1:

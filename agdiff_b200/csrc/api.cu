@@ -109,6 +109,7 @@ static LaunchCtx make_ctx(agd_handle* h) {
   c.stream = h->stream;
   c.num_sms = h->num_sms;
   c.launch_counter = &h->launches;
+  c.prof = nullptr;
   c.cutoff = h->cfg.cutoff;
   c.smooth = h->cfg.smooth_conv;
   c.num_convs = h->cfg.num_convs;
@@ -486,6 +487,7 @@ int agd_op_cfconv_aggregate(const float* x, const float* W, const int32_t* src, 
   LaunchCtx c{};
   c.stream = (cudaStream_t)stream;
   c.launch_counter = &dummy;
+  c.prof = nullptr;
   launch_aggregate(c, x, W, src, in_ptr, n_nodes, F, out);
   CUDA_TRY(cudaGetLastError());
   return AGD_OK;
@@ -525,5 +527,42 @@ int64_t agd_debug_fetch(agd_batch* b, const char* name, float* dst, int64_t capa
 }
 
 int64_t agd_launch_count(const agd_handle* h) { return h ? h->launches : 0; }
+
+int agd_profile_forward(agd_handle* h, agd_batch* b, const float* pos, int32_t with_global, char* labels, int64_t labels_cap,
+                        float* ms, int32_t cap, int32_t* n_out, int32_t* n_edges_out, void* stream) {
+  int rc = check_ready(h, b);
+  if (rc) return rc;
+  if (!pos || !labels || !ms || !n_out) return fail(AGD_ERR_INVALID, "null argument");
+  if ((rc = enter(h, stream))) return rc;
+  LaunchCtx c = make_ctx(h);
+  Prof prof;
+  cudaEvent_t start;
+  CUDA_TRY(cudaEventCreate(&start));
+  CUDA_TRY(cudaEventRecord(start, h->stream));
+  c.prof = &prof;
+  if (with_global) run_global_branch(c, b->d, h->w, pos);
+  run_local_branch(c, b->d, h->w, pos, nullptr);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  std::string names;
+  int n = 0;
+  cudaEvent_t prev = start;
+  for (size_t i = 0; i < prof.ev.size(); ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, prev, prof.ev[i]);
+    if (n < cap) {
+      ms[n++] = t;
+      names += prof.label[i];
+      names += '\n';
+    }
+    prev = prof.ev[i];
+  }
+  cudaEventDestroy(start);
+  for (auto e : prof.ev) cudaEventDestroy(e);
+  if ((int64_t)names.size() + 1 > labels_cap) return fail(AGD_ERR_CAPACITY, "label buffer too small");
+  std::memcpy(labels, names.c_str(), names.size() + 1);
+  *n_out = n;
+  if (n_edges_out) CUDA_TRY(cudaMemcpy(n_edges_out, b->d.counters, sizeof(int), cudaMemcpyDeviceToHost));
+  return leave(h, stream);
+}
 
 }  // extern "C"

@@ -203,6 +203,8 @@ __device__ __forceinline__ float ssp(float x, float beta) {
   return sp - LN2F;
 }
 __device__ __forceinline__ float leaky02(float x) { return x > 0.f ? x : 0.2f * x; }
+// torch.relu propagates NaN (fmaxf would swallow it and hide a diverged trajectory from the NaN guard)
+__device__ __forceinline__ float relu_(float x) { return x < 0.f ? 0.f : x; }
 
 // CFConv cutoff envelope times the learnable distance weight, schnet.py:136-149.
 // dw = [w1(32) | b1(32) | w2(32) | b2]
@@ -211,7 +213,7 @@ __device__ __forceinline__ float cfconv_edge_weight(float d, const float* __rest
 #pragma unroll 8
   for (int j = 0; j < 32; ++j) {
     const float hj = fmaf(__ldg(dw + j), d, __ldg(dw + 32 + j));
-    z = fmaf(__ldg(dw + 64 + j), fmaxf(hj, 0.f), z);
+    z = fmaf(__ldg(dw + 64 + j), relu_(hj), z);
   }
   const float lw = sigmoidf_(z);
   float C;

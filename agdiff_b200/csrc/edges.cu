@@ -237,12 +237,14 @@ void launch_build_edges(const LaunchCtx& c, const BatchDev& b, const float* pos)
   const float r2 = c.cutoff * c.cutoff;
   adjacency_kernel<<<b.n_mols, 128, 0, c.stream>>>(pos, b.mol_ptr, b.st_src, b.st_dst, b.st_in_ptr, r2, b.adj, b.adjT,
                                                    b.in_deg, b.out_deg, b.counters);
+  note_launch(c, "edges.adjacency");
   degree_scan_kernel<<<1, 1024, 0, c.stream>>>(b.in_deg, b.out_deg, b.n_atoms, b.in_ptr, b.out_ptr, b.counters);
+  note_launch(c, "edges.scan");
   const int warps_per_cta = 8;
   edge_fill_kernel<<<(b.n_atoms + warps_per_cta - 1) / warps_per_cta, 256, 0, c.stream>>>(
       pos, b.mol_ptr, b.atom_mol, b.n_atoms, b.st_src, b.st_type, b.st_in_ptr, b.adj, b.adjT, b.in_ptr, b.out_ptr,
       b.e_src, b.e_dst, b.e_type, b.e_canon, b.e_len, b.c_src, b.c_dst, b.c_type, b.c_len);
-  *c.launch_counter += 3;
+  note_launch(c, "edges.fill");
 }
 
 void launch_export_edges(const LaunchCtx& c, const BatchDev& b, const agd_forward_out& out, bool with_scores) {
@@ -251,12 +253,12 @@ void launch_export_edges(const LaunchCtx& c, const BatchDev& b, const agd_forwar
   if (blocks < 1) blocks = 1;
   export_edges_kernel<<<(int)blocks, 256, 0, c.stream>>>(b.counters, b.c_src, b.c_dst, b.c_type, b.c_len, b.s_canon, out,
                                                           with_scores ? 1 : 0);
-  *c.launch_counter += 1;
+  note_launch(c, "export.edges");
   if (with_scores && out.edge_inv_local && b.n_local > 0) {
     int64_t bl = (b.n_local + 255) / 256;
     if (bl > c.num_sms * 8) bl = c.num_sms * 8;
     copy_f32_kernel<<<(int)bl, 256, 0, c.stream>>>(b.sl_canon, out.edge_inv_local, b.n_local);
-    *c.launch_counter += 1;
+    note_launch(c, "export.local");
   }
 }
 

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(NT, 2) pair_mlp_kernel(const PairArgs a) {
     tile_gemm<HID, HID, false>(a.w.P1h, As, Ws, acc, tc.tx, tc.ty);
     tile_load_T<HID>(a.feat, row0, n_rows, HID, 0, As);
     tile_gemm<HID, HID, true>(a.w.P1e, As, Ws, acc, tc.tx, tc.ty);
-    tile_store_smem<HID>(acc, As, tc.tx, tc.ty, [&](float v, int m, int n) { return fmaxf(v + __ldg(a.w.p1b + n), 0.f); });
+    tile_store_smem<HID>(acc, As, tc.tx, tc.ty, [&](float v, int m, int n) { return relu_(v + __ldg(a.w.p1b + n)); });
     float acc2[8][4];
     tile_gemm<HID, 64, false>(a.w.P2, As, Ws, acc2, tc.tx, tc.ty);
     // last Linear (64 -> 1): per-thread partial over its 4 columns, reduce over the 16 tx threads
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(NT, 2) pair_mlp_kernel(const PairArgs a) {
       const int n = tc.tx * 4 + j;
       const float wj = __ldg(a.w.p3w + n), bj = __ldg(a.w.p2b + n);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) part[i] = fmaf(fmaxf(acc2[i][j] + bj, 0.f), wj, part[i]);
+      for (int i = 0; i < 8; ++i) part[i] = fmaf(relu_(acc2[i][j] + bj), wj, part[i]);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -185,7 +185,7 @@ void launch_encoder_global(const LaunchCtx& c, const BatchDev& b, const ModelW& 
   a.e_type = b.e_type;
   a.out = b.g2;
   edge_encoder_kernel<false><<<tiles_grid(b.cap, c.num_sms, 2), NT, ENC_SMEM, c.stream>>>(a);
-  *c.launch_counter += 1;
+  note_launch(c, "encoder.global");
 }
 
 void launch_encoder_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos) {
@@ -203,7 +203,7 @@ void launch_encoder_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w
   a.len_canon = b.lcc_len;
   a.out = b.ea_loc;
   edge_encoder_kernel<true><<<tiles_grid(b.n_local, c.num_sms, 2), NT, ENC_SMEM, c.stream>>>(a);
-  *c.launch_counter += 1;
+  note_launch(c, "encoder.local");
 }
 
 void launch_pair_global(const LaunchCtx& c, const BatchDev& b, const ModelW& w) {
@@ -218,7 +218,7 @@ void launch_pair_global(const LaunchCtx& c, const BatchDev& b, const ModelW& w) 
   a.s_csc = b.s_csc;
   a.s_canon = b.s_canon;
   pair_mlp_kernel<<<tiles_grid(b.cap, c.num_sms, 2), NT, PAIR_SMEM, c.stream>>>(a);
-  *c.launch_counter += 1;
+  note_launch(c, "pair.global");
 }
 
 void launch_pair_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* h_local) {
@@ -235,7 +235,7 @@ void launch_pair_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w, c
   a.s_csc = b.sl_csc;
   a.s_canon = b.sl_canon;
   pair_mlp_kernel<<<tiles_grid(b.n_local, c.num_sms, 2), NT, PAIR_SMEM, c.stream>>>(a);
-  *c.launch_counter += 1;
+  note_launch(c, "pair.local");
 }
 
 void set_encoder_attributes() {

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(NT, 2) gin_layer_kernel(const GinArgs a) {
         const float* xs = a.x_in + (size_t)__ldg(a.src + e) * HID;
         const float* ee = a.ea + (size_t)e * HID;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] += fmaxf(__ldg(xs + lane + 32 * j) + __ldg(ee + lane + 32 * j), 0.f);
+        for (int j = 0; j < 4; ++j) v[j] += relu_(__ldg(xs + lane + 32 * j) + __ldg(ee + lane + 32 * j));
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = fmaf(ope, self[j], v[j]);
@@ -61,12 +61,12 @@ __global__ void __launch_bounds__(NT, 2) gin_layer_kernel(const GinArgs a) {
   }
   float acc[8][8];
   tile_gemm<HID, HID, false>(a.w.G1, As, Ws, acc, tc.tx, tc.ty);
-  tile_store_smem<HID>(acc, As, tc.tx, tc.ty, [&](float v, int m, int n) { return fmaxf(v + __ldg(a.w.g1b + n), 0.f); });
+  tile_store_smem<HID>(acc, As, tc.tx, tc.ty, [&](float v, int m, int n) { return relu_(v + __ldg(a.w.g1b + n)); });
   tile_gemm<HID, HID, false>(a.w.G2, As, Ws, acc, tc.tx, tc.ty);
   const int last = a.last;
   tile_store_global<HID>(acc, a.x_out, row0, n_rows, HID, 0, tc.tx, tc.ty, [&](float v, int m, int n) {
     float o = v + __ldg(a.w.g2b + n);
-    if (!last) o = fmaxf(o, 0.f);
+    if (!last) o = relu_(o);
     return o + __ldg(a.x_in + (size_t)(row0 + m) * HID + n);
   });
 }
@@ -76,7 +76,7 @@ void launch_gin_embed(const LaunchCtx& c, const BatchDev& b, const ModelW& w) {
   if (blocks > c.num_sms * 8) blocks = c.num_sms * 8;
   if (blocks < 1) blocks = 1;
   gin_embed_kernel<<<(int)blocks, 256, 0, c.stream>>>(w.gin_emb, b.atom_type, b.n_atoms, b.gx0);
-  *c.launch_counter += 1;
+  note_launch(c, "gin.embed");
 }
 
 void launch_gin_layer(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int layer, const float* x_in, float* x_out) {
@@ -90,7 +90,7 @@ void launch_gin_layer(const LaunchCtx& c, const BatchDev& b, const ModelW& w, in
   a.n_nodes = b.n_atoms;
   a.last = (layer == c.num_convs_local - 1) ? 1 : 0;
   gin_layer_kernel<<<(b.n_atoms + TM - 1) / TM, NT, GIN_SMEM, c.stream>>>(a);
-  *c.launch_counter += 1;
+  note_launch(c, "gin.layer");
 }
 
 void set_gin_attributes() {

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/agdiff_b200.h"
 
 namespace agd {
@@ -92,10 +94,17 @@ struct StepParams {
   int step_offset;  // added to the device step counter for the Philox stream
 };
 
+// optional per-launch CUDA-event trace (agd_profile_forward)
+struct Prof {
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> label;
+};
+
 struct LaunchCtx {
   cudaStream_t stream;
   int num_sms;
   int64_t* launch_counter;
+  Prof* prof;
   float cutoff;
   int smooth;
   int num_convs, num_convs_local;
@@ -126,6 +135,16 @@ void launch_advance(const LaunchCtx& c, const BatchDev& b);
 void launch_eq_transform(cudaStream_t s, const float* score, const float* pos, const int* src, const int* dst,
                          const float* len, int64_t n_edges, int n_nodes, float* out);
 
-void set_kernel_attributes();   // opt-in dynamic shared memory sizes; called once per process
+// bookkeeping after every kernel launch: count it and, when tracing, drop an event behind it
+inline void note_launch(const LaunchCtx& c, const char* label) {
+  *c.launch_counter += 1;
+  if (c.prof) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, c.stream);
+    c.prof->ev.push_back(e);
+    c.prof->label.push_back(label);
+  }
+}
 
 }  // namespace agd

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(NT, 1) schnet_node_kernel(const NodeArgs a) {
         const int n = tc.tx * 4 + j;
         const float wj = __ldg(a.w.a2w + n), bj = __ldg(a.w.a1b + n);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) part[i] = fmaf(fmaxf(acc2[i][j] + bj, 0.f), wj, part[i]);
+        for (int i = 0; i < 8; ++i) part[i] = fmaf(relu_(acc2[i][j] + bj), wj, part[i]);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(NT, 1) schnet_node_kernel(const NodeArgs a) {
       float s = 0.f;
 #pragma unroll 8
       for (int k = 0; k < HID; ++k) s = fmaf(As[k * LDA + m], __ldg(a.w.S1 + k * 8 + j), s);
-      s_r8[j * TM + m] = fmaxf(s, 0.f);
+      s_r8[j * TM + m] = relu_(s);
     }
     __syncthreads();
     {
@@ -259,9 +259,10 @@ void launch_filters(const LaunchCtx& c, const BatchDev& b, const ModelW& mw, int
   a.smooth = c.smooth;
   a.F1 = w.F1a; a.f1b = w.f1ab; a.F2 = w.F2a; a.f2b = w.f2ab; a.dw = w.dw1; a.beta_ptr = w.sc + 0; a.col0 = 0;
   filter_kernel<128><<<tiles_grid(b.cap, c.num_sms, 2), NT, FILT_SMEM, c.stream>>>(a);
+  note_launch(c, "schnet.filter128");
   a.F1 = w.F1b; a.f1b = w.f1bb; a.F2 = w.F2b; a.f2b = w.f2bb; a.dw = w.dw2; a.beta_ptr = w.sc + 1; a.col0 = 128;
   filter_kernel<64><<<tiles_grid(b.cap, c.num_sms, 2), NT, FILT_SMEM, c.stream>>>(a);
-  *c.launch_counter += 2;
+  note_launch(c, "schnet.filter64");
 }
 
 void launch_aggregate(const LaunchCtx& c, const float* x, const float* W, const int* src, const int* in_ptr, int n_nodes,
@@ -274,7 +275,7 @@ void launch_aggregate(const LaunchCtx& c, const float* x, const float* W, const 
     cfconv_aggregate_kernel<128><<<blocks, 128, 0, c.stream>>>(x, W, src, in_ptr, n_nodes, out);
   else
     cfconv_aggregate_kernel<64><<<blocks, 64, 0, c.stream>>>(x, W, src, in_ptr, n_nodes, out);
-  *c.launch_counter += 1;
+  note_launch(c, "schnet.aggregate");
 }
 
 void launch_schnet_node(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk) {
@@ -293,7 +294,7 @@ void launch_schnet_node(const LaunchCtx& c, const BatchDev& b, const ModelW& w, 
   }
   const int blocks = (b.n_atoms + TM - 1) / TM;
   schnet_node_kernel<<<blocks, NT, NODE_SMEM, c.stream>>>(a);
-  *c.launch_counter += 1;
+  note_launch(c, "schnet.node");
 }
 
 void set_schnet_attributes() {

@@ -190,12 +190,12 @@ void launch_step(const LaunchCtx& c, const BatchDev& b, float* pos, const StepPa
   a.counters = b.counters;
   a.p = p;
   langevin_step_kernel<<<b.n_mols, STEP_THREADS, 0, c.stream>>>(a);
-  *c.launch_counter += 1;
+  note_launch(c, "step.langevin");
 }
 
 void launch_advance(const LaunchCtx& c, const BatchDev& b) {
   advance_step_kernel<<<1, 1, 0, c.stream>>>(b.counters);
-  *c.launch_counter += 1;
+  note_launch(c, "step.advance");
 }
 
 // stand-alone eq_transform over an arbitrary edge list (microbenchmark iii / module parity):

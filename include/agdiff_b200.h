@@ -160,6 +160,12 @@ int agd_op_eq_transform(const float* score /*dev [E]*/, const float* pos, const 
  * "g2", "h_global", "h_local", "ea_local", "xcat", "agg", "filt".  Returns element count or <0. */
 int64_t agd_debug_fetch(agd_batch* b, const char* name, float* dst_dev, int64_t capacity);
 
+/* measurement: run the per-step network evaluation once (no position update) with a CUDA event
+ * behind every kernel launch on the launching stream; ms[i] is the device time of launch i and
+ * labels receives the '\n'-separated kernel labels.  n_edges_out (host) gets the edge count. */
+int agd_profile_forward(agd_handle* h, agd_batch* b, const float* pos_dev, int32_t with_global, char* labels,
+                        int64_t labels_cap, float* ms, int32_t cap, int32_t* n_out, int32_t* n_edges_out, void* stream);
+
 /* number of kernel launches issued by the library since the handle was created */
 int64_t agd_launch_count(const agd_handle* h);
 

@@ -31,6 +31,14 @@ def _cuda_model(cfg_name, seed=2021, perturb=0, **cfg_over):
     return m.to(DEV), sd
 
 
+def _settle(m):
+    """nn.Embedding(max_norm=10) rescales looked-up rows in place on every call (reference schnet.py:254);
+    the first rescale can land an ulp above 10, so iterate to the fixed point before bitwise comparisons."""
+    idx = torch.arange(100, device=DEV)
+    for _ in range(4):
+        m._renorm_embedding(idx)
+
+
 def _batch(kind, seed=0, scale=2.5, repeats=1):
     if kind == "alanine":
         mols = [graph.extend_bond_order_host(synth.alanine_dipeptide())]
@@ -162,6 +170,8 @@ def test_forward_reduced_depth(num_convs, num_convs_local):
 def test_forward_extend_order_default():
     """forward's default extend_order=True: bond graph in, 2-/3-hop edges added on device"""
     m, sd = _cuda_model("qm9", 2021, 2)
+    _settle(m)
+    sd = state_dict_cpu(m)
     mols = synth.qm9_like(5, seed=9) + [synth.alanine_dipeptide()]
     z, bi, bt, b, G = graph.collate(mols, 1)
     pos = torch.randn(z.numel(), 3, generator=torch.Generator().manual_seed(4)) * 2.0
@@ -195,6 +205,7 @@ def test_state_dict_roundtrip_and_renorm_side_effect():
 def test_trajectory_matches_reference_golden(name):
     g = golden(name)
     m, sd = _cuda_model(g["cfg_name"], g["seed"], 0)
+    _settle(m)
     n_steps = g["n_steps"]
     noise = torch.randn(n_steps, g["atom_type"].numel(), 3, generator=torch.Generator().manual_seed(g["noise_seed"]))
     G = int(g["batch"].max()) + 1
@@ -237,6 +248,7 @@ def test_trajectory_drugs_vs_oracle():
 
 def test_sampler_properties():
     m, sd = _cuda_model("qm9", 2021, 0)
+    _settle(m)
     z, bi, bt, b, G, pos = _batch("qm9", seed=6, scale=1.0)
     args = (z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), G)
     kw = dict(extend_order=False, n_steps=20, step_lr=1e-6, clip=1000.0, clip_local=20.0, global_start_sigma=0.5,
@@ -265,8 +277,7 @@ def test_device_noise_statistics():
     m, sd = _cuda_model("qm9", 2021, 0)
     mols = [graph.extend_bond_order_host(x) for x in synth.qm9_like(400, seed=1)]
     z, bi, bt, b, G = graph.collate(mols, 1)
-    pos0 = torch.zeros(z.numel(), 3)
-    pos0[:, 0] = torch.arange(z.numel()) % 7 * 0.01 + 0.01     # distinct positions (non-zero lengths)
+    pos0 = torch.randn(z.numel(), 3, generator=torch.Generator().manual_seed(2))   # distinct atoms: non-zero lengths
     pos, _ = m.langevin_dynamics_sample_diffusion(z.to(DEV), pos0.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), G,
                                                   extend_order=False, n_steps=1, step_lr=1e-6, clip=1000.0,
                                                   clip_local=0.0, global_start_sigma=0.0, w_global=0.0, seed=5,
