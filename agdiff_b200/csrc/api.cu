@@ -3,6 +3,7 @@
 // local+global step).  No CPU fallback: every entry point needs a CUDA device.
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,6 +15,7 @@ namespace agd {
 void set_encoder_attributes();
 void set_schnet_attributes();
 void set_gin_attributes();
+void set_tc_attributes();
 }  // namespace agd
 
 using namespace agd;
@@ -46,6 +48,7 @@ struct agd_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   int64_t launches = 0;
+  int use_tc = 1;
 };
 
 struct agd_batch {
@@ -86,6 +89,8 @@ static void build_slots(agd_handle* h) {
     add(p + "a2w", 64, &b.a2w);
     add(p + "S1", H * 8, &b.S1);       add(p + "S2", 8 * H, &b.S2);
     add(p + "sc", 4, &b.sc);
+    add(p + "tF1a", 2 * 128 * 128, &b.tF1a); add(p + "tF2a", 2 * 128 * 128, &b.tF2a);
+    add(p + "tF1b", 2 * 64 * 128, &b.tF1b);   add(p + "tF2b", 2 * 64 * 64, &b.tF2b);
   }
   auto add_pair = [&](const std::string& p, PairW& q) {
     add(p + "P1h", H * H, &q.P1h); add(p + "P1e", H * H, &q.P1e); add(p + "p1b", H, &q.p1b);
@@ -110,6 +115,7 @@ static LaunchCtx make_ctx(agd_handle* h) {
   c.num_sms = h->num_sms;
   c.launch_counter = &h->launches;
   c.prof = nullptr;
+  c.use_tc = h->use_tc;
   c.cutoff = h->cfg.cutoff;
   c.smooth = h->cfg.smooth_conv;
   c.num_convs = h->cfg.num_convs;
@@ -186,6 +192,8 @@ int agd_create(const agd_config* cfg, agd_handle** out) {
   set_encoder_attributes();
   set_schnet_attributes();
   set_gin_attributes();
+  set_tc_attributes();
+  if (const char* e = std::getenv("AGD_TC_FILTERS")) h->use_tc = (e[0] != '0');
   CUDA_TRY(cudaGetLastError());
   *out = h;
   return AGD_OK;
@@ -488,6 +496,7 @@ int agd_op_cfconv_aggregate(const float* x, const float* W, const int32_t* src, 
   c.stream = (cudaStream_t)stream;
   c.launch_counter = &dummy;
   c.prof = nullptr;
+  c.use_tc = 0;
   launch_aggregate(c, x, W, src, in_ptr, n_nodes, F, out);
   CUDA_TRY(cudaGetLastError());
   return AGD_OK;

@@ -31,6 +31,7 @@ struct BlkW {              // InteractionBlock k, schnet.py:165-216 (+ scaling m
   const float *A1, *a1b, *a2w;               // attention: [128][64], [64], [64]
   const float *S1, *S2;                      // scaling fc: [128][8], [8][128]
   const float *sc;                           // scalars: beta(conv1.nn.1), beta(conv2.nn.1), beta(act), attention.2.bias
+  const float *tF1a, *tF2a, *tF1b, *tF2b;    // tcgen05 operand images of the filter nets: [hi | lo], K-major SWIZZLE_128B
 };
 struct PairW {             // grad_{global,local}_dist_mlp, common.py:86-103 on [h_row*h_col, edge_attr]
   const float *P1h, *P1e, *p1b;   // layers.0 split: [128][128] on h_row*h_col, [128][128] on g2 (global, merged) / edge_attr (local)
@@ -105,6 +106,7 @@ struct LaunchCtx {
   int num_sms;
   int64_t* launch_counter;
   Prof* prof;
+  int use_tc;      // 1: CFConv filter nets on tcgen05 (3xTF32), 0: fp32 FFMA tile kernels
   float cutoff;
   int smooth;
   int num_convs, num_convs_local;
@@ -123,6 +125,7 @@ void launch_pair_global(const LaunchCtx& c, const BatchDev& b, const ModelW& w);
 void launch_pair_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* h_local);
 // schnet.cu
 void launch_filters(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);
+void launch_filters_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);   // tc_filter.cu
 void launch_aggregate(const LaunchCtx& c, const float* x, const float* W, const int* src, const int* in_ptr, int n_nodes,
                       int F, float* out);
 void launch_schnet_node(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk /* -1: embedding + first lin1 */);

@@ -249,6 +249,10 @@ static int tiles_grid(int64_t rows_cap, int num_sms, int per_sm) {
 }
 
 void launch_filters(const LaunchCtx& c, const BatchDev& b, const ModelW& mw, int blk) {
+  if (c.use_tc) {
+    launch_filters_tc(c, b, mw, blk);
+    return;
+  }
   const BlkW& w = mw.blk[blk];
   FiltArgs a{};
   a.n_rows_dev = b.counters;

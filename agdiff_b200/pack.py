@@ -37,6 +37,27 @@ def _fold_bn(sd, lin_key, bn_key):
     return (w * s[:, None]).T.copy(), (b - mean) * s + beta      # [K][N], [N]
 
 
+def umma_image(W: np.ndarray) -> np.ndarray:
+    """tcgen05 B-operand image of a Linear weight W[N][K] (N = out, K = in, i.e. K-major): fp32 split into
+    TF32-representable hi = w & 0xffffe000 and lo = fl32(w - hi) & 0xffffe000, each laid out as the canonical
+    K-major SWIZZLE_128B shared-memory layout the UMMA descriptor in csrc/tc_filter.cu describes: K in atoms of
+    32 floats (128 B rows), per atom N rows of 128 B, 16-byte chunk c of row n stored at chunk c ^ (n % 8).
+    Returns [hi image | lo image] as float32 bit patterns."""
+    w32 = np.ascontiguousarray(W, dtype=np.float64).astype(np.float32)
+    N, K = w32.shape
+    assert K % 32 == 0 and N % 8 == 0
+    bits = w32.view(np.uint32)
+    hi = (bits & np.uint32(0xFFFFE000)).view(np.float32)
+    lo = ((w32 - hi).astype(np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    n = np.arange(N)[:, None]
+    k = np.arange(K)[None, :]
+    off = (k // 32) * (N * 32) + n * 32 + ((((k % 32) // 4) ^ (n % 8)) * 4) + (k % 4)
+    out = np.zeros(2 * N * K, dtype=np.float32)
+    out[off.reshape(-1)] = hi.reshape(-1)
+    out[N * K + off.reshape(-1)] = lo.reshape(-1)
+    return out
+
+
 def fold_state_dict(sd: Dict[str, torch.Tensor], num_convs: int, num_convs_local: int) -> Dict[str, np.ndarray]:
     """-> {slot name: float64 array}."""
     out: Dict[str, np.ndarray] = {}
@@ -72,6 +93,8 @@ def fold_state_dict(sd: Dict[str, torch.Tensor], num_convs: int, num_convs_local
             out[p + "F1" + tag] = (w0 @ C2).T
             out[p + "f1%sb" % tag] = w0 @ cb2 + b0
             out[p + "F2" + tag] = _f64(sd[cp + "nn.2.weight"]).T
+            out[p + "tF1" + tag] = umma_image(w0 @ C2)                       # W[N=out][K=in]
+            out[p + "tF2" + tag] = umma_image(_f64(sd[cp + "nn.2.weight"]))
             out[p + "f2%sb" % tag] = _f64(sd[cp + "nn.2.bias"])
             dw = np.zeros(128)
             dw[0:32] = _f64(sd[cp + "distance_weighting.layer1.weight"])[:, 0]
