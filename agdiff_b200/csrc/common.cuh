@@ -228,6 +228,27 @@ __device__ __forceinline__ float cfconv_edge_weight(float d, const float* __rest
   return lw * C;
 }
 
+// same, with the distance MLP already staged in shared memory
+__device__ __forceinline__ float cfconv_edge_weight_smem(float d, const float* dw, float cutoff, int smooth) {
+  float z = dw[96];
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) {
+    const float hj = fmaf(dw[j], d, dw[32 + j]);
+    z = fmaf(dw[64 + j], relu_(hj), z);
+  }
+  const float lw = sigmoidf_(z);
+  float C;
+  if (smooth) {
+    C = 0.5f * (cosf(d * 3.14159265358979323846f / cutoff) + 1.0f);
+    C = (d <= cutoff) ? C : 0.f;
+  } else {
+    const float t = d - cutoff;
+    C = expf(-(t * t) / (2.0f * cutoff * cutoff));
+  }
+  C = (d <= cutoff && d >= 0.f) ? C : 0.f;
+  return lw * C;
+}
+
 __device__ __forceinline__ float block_rows_tail_guard(int64_t r, int64_t n) { return r < n ? 1.f : 0.f; }
 
 }  // namespace agd

@@ -6,9 +6,9 @@
 // GEMM is 3xTF32:  A.B ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi  with x_hi = x & 0xffffe000 (what the tensor
 // core reads anyway) and x_lo = x - x_hi (exact in fp32), accumulated in fp32 in TMEM.
 //
-// Data flow of one 128-edge tile (one CTA per SM, 256 threads, 512 TMEM columns):
+// Data flow of one 128-edge tile (one CTA per SM, 512 threads, 512 TMEM columns):
 //   * the activation operand lives in TENSOR MEMORY (tcgen05.mma with A from TMEM): thread (warp w, lane l) owns
-//     TMEM lane 32*(w%4)+l = tile row, warps 0-3 / 4-7 own the two column halves.  g2 rows are split in registers
+//     TMEM lane 32*(w%4)+l = tile row, the four warp groups own one quarter of the columns each.  g2 rows are split in registers
 //     and tcgen05.st'd as A_hi (cols 128..255) / A_lo (cols 256..383); the layer-1 accumulator D (cols 0..127)
 //     is read back with tcgen05.ld, bias + ShiftedSoftplus applied, split again and stored over A for layer 2.
 //     The MLP chain never touches shared or global memory.
@@ -16,97 +16,11 @@
 //     streams it from L2 with cp.async.bulk + mbarrier complete_tx into a single 128 KB buffer: layer-2 weights
 //     are fetched while the layer-1 epilogue runs, the next tile's layer-1 weights during the layer-2 epilogue.
 //   * one elected thread issues the 3 x K/8 tcgen05.mma (M=128, N=F, K=8) per layer and tcgen05.commit's to an
-//     mbarrier that the 256 epilogue threads wait on.
-#include "common.cuh"
+//     mbarrier that the 512 epilogue threads wait on.
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace agd {
-namespace tc {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra LAB_WAIT;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 1-D bulk copy global -> shared, completion reported to an mbarrier (async proxy, like TMA)
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::); }
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(addr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(addr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
-      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 B, 8-row groups
-// 1024 B apart (SBO), LBO unused (=1), descriptor version 1 (Blackwell), layout type 2.
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
-  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-  return (static_cast<uint64_t>(hi) << 32) | lo;
-}
-// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, TF32 x TF32, both K-major, M=128
-__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
-}
-// D[tmem] (+)= A[tmem] . B[smem]^T, issued by ONE thread
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-constexpr uint32_t TF32_MASK = 0xFFFFE000u;
-constexpr int COL_D = 0, COL_AHI = 128, COL_ALO = 256, TMEM_COLS = 512;
-
-}  // namespace tc
 
 struct TcFiltArgs {
   const float* W1img;   // [hi | lo] swizzled K-major images of F1: each (128/32) x F rows x 128 B
@@ -120,24 +34,28 @@ struct TcFiltArgs {
   int smooth;
 };
 
-constexpr size_t TC_FILT_SMEM = 1024 /*align slack*/ + 131072 /*weights hi|lo*/ + 128 * sizeof(float) + 64;
+constexpr int TC_THREADS = 512;
+constexpr size_t TC_FILT_SMEM = 1024 /*align slack*/ + 131072 /*weights hi|lo*/ + (128 + 128 + 128 + 128) * sizeof(float) + 64;
 
 template <int F>
-__global__ void __launch_bounds__(256, 1) tc_filter_kernel(const TcFiltArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltArgs a) {
   using namespace tc;
   constexpr uint32_t W1_HALF = (HID / 32) * F * 128;   // bytes of one (hi or lo) image of F1: K=128
   constexpr uint32_t W2_HALF = (F / 32) * F * 128;     // K=F
-  constexpr int HALF_COLS = F / 2;                     // columns owned by one warp group
-  constexpr int CHUNKS = HALF_COLS / 16;
+  constexpr int PART_COLS = F / 4;                     // output columns owned by one of the 4 warp groups
+  constexpr int CHUNKS = PART_COLS / 16;               // 2 (F=128) or 1 (F=64)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* wbuf = base;                                             // 128 KB, 1024-aligned
-  float* s_cw = reinterpret_cast<float*>(base + 131072);            // [128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_cw + 128);         // [0]=weights landed, [1]=mma done
+  float* s_cw = reinterpret_cast<float*>(base + 131072);            // [128] envelope weight of each tile row
+  float* s_b1 = s_cw + 128;                                         // [F] layer-1 bias
+  float* s_b2 = s_b1 + 128;                                         // [F] layer-2 bias
+  float* s_dw = s_b2 + 128;                                         // [128] distance-weighting MLP
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dw + 128);         // [0]=weights landed, [1]=mma done
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, half = warp >> 2;
+  const int quad = warp & 3, part = warp >> 2;
   const int my_row = quad * 32 + lane;
   const int n_rows = *a.n_rows_dev;
   const int n_tiles = (n_rows + TM - 1) / TM;
@@ -151,6 +69,11 @@ __global__ void __launch_bounds__(256, 1) tc_filter_kernel(const TcFiltArgs a) {
     mbar_init(&bars[1], 1);
     fence_barrier_init();
   }
+  if (tid < F) {
+    s_b1[tid] = __ldg(a.f1b + tid);
+    s_b2[tid] = __ldg(a.f2b + tid);
+  }
+  if (tid < 128) s_dw[tid] = __ldg(a.dw + tid);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -177,22 +100,38 @@ __global__ void __launch_bounds__(256, 1) tc_filter_kernel(const TcFiltArgs a) {
     }
     mma_commit(&bars[1]);
   };
+  // this thread's slice of a g2 row: 32 input features = 8 x float4, kept in registers one tile ahead
+  float4 pre[8];
+  float pre_len = 0.f;
+  auto prefetch = [&](int t) {
+    const int64_t r = static_cast<int64_t>(t) * TM + my_row;
+    if (t < n_tiles && r < n_rows) {
+      const float4* src = reinterpret_cast<const float4*>(a.g2 + r * HID + part * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pre[q] = __ldg(src + q);
+      pre_len = __ldg(a.e_len + r);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pre[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pre_len = -1.f;
+    }
+  };
 
   if (tid == 0 && blockIdx.x < n_tiles) load_weights(a.W1img, W1_HALF);
+  prefetch(blockIdx.x);
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = static_cast<int64_t>(tile) * TM;
     const int64_t r = row0 + my_row;
     const bool valid = r < n_rows;
-    // ---- stage A = g2 tile (hi/lo) into TMEM; per-edge envelope weight into smem
-    if (half == 0) s_cw[my_row] = valid ? cfconv_edge_weight(a.e_len[r], a.dw, a.cutoff, a.smooth) : 0.f;
+    // ---- stage A = g2 tile (hi/lo) into TMEM from the prefetched registers; envelope weight into smem
+    if (part == 3) s_cw[my_row] = valid ? cfconv_edge_weight_smem(pre_len, s_dw, a.cutoff, a.smooth) : 0.f;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {   // K = 128 input features: each warp group stores 64 columns
+    for (int c = 0; c < 2; ++c) {
       uint32_t hi[16], lo[16];
-      const float4* src = reinterpret_cast<const float4*>(a.g2 + r * HID + half * 64 + c * 16);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 v = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 v = pre[c * 4 + q];
         const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -201,8 +140,8 @@ __global__ void __launch_bounds__(256, 1) tc_filter_kernel(const TcFiltArgs a) {
           lo[q * 4 + j] = __float_as_uint(vv[j] - __uint_as_float(h));
         }
       }
-      tmem_st16(trow + COL_AHI + half * 64 + c * 16, hi);
-      tmem_st16(trow + COL_ALO + half * 64 + c * 16, lo);
+      tmem_st16(trow + COL_AHI + part * 32 + c * 16, hi);
+      tmem_st16(trow + COL_ALO + part * 32 + c * 16, lo);
     }
     wait_st();
     fence_before_sync();
@@ -214,6 +153,7 @@ __global__ void __launch_bounds__(256, 1) tc_filter_kernel(const TcFiltArgs a) {
       issue_layer(HID, W1_HALF);
     }
     w_phase ^= 1;
+    prefetch(tile + static_cast<int>(gridDim.x));    // next tile's operand rows travel while the tensor core works
     mbar_wait(&bars[1], m_phase);
     m_phase ^= 1;
     fence_after_sync();
@@ -222,12 +162,12 @@ __global__ void __launch_bounds__(256, 1) tc_filter_kernel(const TcFiltArgs a) {
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
       uint32_t v[16], hi[16], lo[16];
-      const int n0 = half * HALF_COLS + c * 16;
+      const int n0 = part * PART_COLS + c * 16;
       tmem_ld16(trow + COL_D + n0, v);
       wait_ld();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float t = ssp(__uint_as_float(v[j]) + __ldg(a.f1b + n0 + j), beta);
+        const float t = ssp_fast(__uint_as_float(v[j]) + s_b1[n0 + j], beta);
         const uint32_t h = __float_as_uint(t) & TF32_MASK;
         hi[j] = h;
         lo[j] = __float_as_uint(t - __uint_as_float(h));
@@ -254,7 +194,7 @@ __global__ void __launch_bounds__(256, 1) tc_filter_kernel(const TcFiltArgs a) {
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
       uint32_t v[16];
-      const int n0 = half * HALF_COLS + c * 16;
+      const int n0 = part * PART_COLS + c * 16;
       tmem_ld16(trow + COL_D + n0, v);
       wait_ld();
       if (valid) {
@@ -262,11 +202,11 @@ __global__ void __launch_bounds__(256, 1) tc_filter_kernel(const TcFiltArgs a) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float4 o;
-          o.x = (__uint_as_float(v[q * 4 + 0]) + __ldg(a.f2b + n0 + q * 4 + 0)) * cw;
-          o.y = (__uint_as_float(v[q * 4 + 1]) + __ldg(a.f2b + n0 + q * 4 + 1)) * cw;
-          o.z = (__uint_as_float(v[q * 4 + 2]) + __ldg(a.f2b + n0 + q * 4 + 2)) * cw;
-          o.w = (__uint_as_float(v[q * 4 + 3]) + __ldg(a.f2b + n0 + q * 4 + 3)) * cw;
-          dst[q] = o;
+          o.x = (__uint_as_float(v[q * 4 + 0]) + s_b2[n0 + q * 4 + 0]) * cw;
+          o.y = (__uint_as_float(v[q * 4 + 1]) + s_b2[n0 + q * 4 + 1]) * cw;
+          o.z = (__uint_as_float(v[q * 4 + 2]) + s_b2[n0 + q * 4 + 2]) * cw;
+          o.w = (__uint_as_float(v[q * 4 + 3]) + s_b2[n0 + q * 4 + 3]) * cw;
+          __stcs(dst + q, o);
         }
       }
     }
@@ -290,10 +230,10 @@ void launch_filters_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& mw, 
   int64_t tiles = (b.cap + TM - 1) / TM;
   const int grid = (int)(tiles < c.num_sms ? (tiles < 1 ? 1 : tiles) : c.num_sms);
   a.W1img = w.tF1a; a.W2img = w.tF2a; a.f1b = w.f1ab; a.f2b = w.f2ab; a.dw = w.dw1; a.beta_ptr = w.sc + 0; a.col0 = 0;
-  tc_filter_kernel<128><<<grid, 256, TC_FILT_SMEM, c.stream>>>(a);
+  tc_filter_kernel<128><<<grid, TC_THREADS, TC_FILT_SMEM, c.stream>>>(a);
   note_launch(c, "schnet.filter128_tc");
   a.W1img = w.tF1b; a.W2img = w.tF2b; a.f1b = w.f1bb; a.f2b = w.f2bb; a.dw = w.dw2; a.beta_ptr = w.sc + 1; a.col0 = 128;
-  tc_filter_kernel<64><<<grid, 256, TC_FILT_SMEM, c.stream>>>(a);
+  tc_filter_kernel<64><<<grid, TC_THREADS, TC_FILT_SMEM, c.stream>>>(a);
   note_launch(c, "schnet.filter64_tc");
 }
 
