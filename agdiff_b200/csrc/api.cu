@@ -16,6 +16,7 @@ void set_encoder_attributes();
 void set_schnet_attributes();
 void set_gin_attributes();
 void set_tc_attributes();
+void set_tc_mlp_attributes();
 }  // namespace agd
 
 using namespace agd;
@@ -71,6 +72,9 @@ static void build_slots(agd_handle* h) {
   add("enc.M2", H * H, &w.enc.M2);
   add("enc.C2", H * H, &w.enc.C2);
   add("enc.c2b", H, &w.enc.c2b);
+  add("tenc.W1", 2 * H * H, &w.tenc_W1); add("tenc.M2", 2 * H * H, &w.tenc_M2); add("tenc.C2", 2 * H * H, &w.tenc_C2);
+  add("tpg.P1h", 2 * H * H, &w.tpg_P1h); add("tpg.P1e", 2 * H * H, &w.tpg_P1e); add("tpg.P2", 2 * 64 * H, &w.tpg_P2);
+  add("tpl.P1h", 2 * H * H, &w.tpl_P1h); add("tpl.P1e", 2 * H * H, &w.tpl_P1e); add("tpl.P2", 2 * 64 * H, &w.tpl_P2);
   add("sch.emb", 100 * H, &w.sch_emb);
   for (int k = 0; k < h->cfg.num_convs; ++k) {
     BlkW& b = w.blk[k];
@@ -139,7 +143,7 @@ static int leave(agd_handle* h, void* user_stream) {
 
 // ------------------------------------------------------------------ launch sequences
 static void run_local_branch(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos, const float** h_out) {
-  launch_encoder_local(c, b, w, pos);
+  if (c.use_tc) launch_encoder_local_tc(c, b, w, pos); else launch_encoder_local(c, b, w, pos);
   launch_gin_embed(c, b, w);
   const float* x_in = b.gx0;
   float* x_out = b.gx1;
@@ -149,20 +153,20 @@ static void run_local_branch(const LaunchCtx& c, const BatchDev& b, const ModelW
     x_in = x_out;
     x_out = const_cast<float*>(t);
   }
-  launch_pair_local(c, b, w, x_in);
+  if (c.use_tc) launch_pair_local_tc(c, b, w, x_in); else launch_pair_local(c, b, w, x_in);
   if (h_out) *h_out = x_in;
 }
 
 static void run_global_branch(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos) {
   launch_build_edges(c, b, pos);
-  launch_encoder_global(c, b, w);
+  if (c.use_tc) launch_encoder_global_tc(c, b, w); else launch_encoder_global(c, b, w);
   launch_schnet_node(c, b, w, -1);
   for (int k = 0; k < c.num_convs; ++k) {
     launch_filters(c, b, w, k);
     launch_aggregate(c, b.xcat, b.filt, b.e_src, b.in_ptr, b.n_atoms, 192, b.agg);
     launch_schnet_node(c, b, w, k);
   }
-  launch_pair_global(c, b, w);
+  if (c.use_tc) launch_pair_global_tc(c, b, w); else launch_pair_global(c, b, w);
 }
 
 extern "C" {
@@ -193,6 +197,7 @@ int agd_create(const agd_config* cfg, agd_handle** out) {
   set_schnet_attributes();
   set_gin_attributes();
   set_tc_attributes();
+  set_tc_mlp_attributes();
   if (const char* e = std::getenv("AGD_TC_FILTERS")) h->use_tc = (e[0] != '0');
   CUDA_TRY(cudaGetLastError());
   *out = h;

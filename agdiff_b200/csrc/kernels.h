@@ -44,6 +44,9 @@ struct GinW {              // GINEConv + BatchNorm, gin.py:38-69,112-148
 };
 struct ModelW {
   EncW enc;
+  const float *tenc_W1, *tenc_M2, *tenc_C2;            // tcgen05 [hi|lo] images of the encoder matrices
+  const float *tpg_P1h, *tpg_P1e, *tpg_P2;              // ... of the global pair MLP
+  const float *tpl_P1h, *tpl_P1e, *tpl_P2;              // ... of the local pair MLP
   const float* sch_emb;   // [100][128], max_norm renorm pre-applied
   BlkW blk[MAX_BLOCKS];
   PairW pg, pl;
@@ -126,6 +129,11 @@ void launch_pair_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w, c
 // schnet.cu
 void launch_filters(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);
 void launch_filters_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);   // tc_filter.cu
+// tc_mlp.cu
+void launch_encoder_global_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w);
+void launch_encoder_local_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos);
+void launch_pair_global_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w);
+void launch_pair_local_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* h_local);
 void launch_aggregate(const LaunchCtx& c, const float* x, const float* W, const int* src, const int* in_ptr, int n_nodes,
                       int F, float* out);
 void launch_schnet_node(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk /* -1: embedding + first lin1 */);

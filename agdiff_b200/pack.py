@@ -75,6 +75,9 @@ def fold_state_dict(sd: Dict[str, torch.Tensor], num_convs: int, num_convs_local
     out["enc.M2"] = (C1[:, :H] @ L2).T
     out["enc.T2"] = bond @ C1[:, H:].T + (C1[:, :H] @ b2 + cb1)
     out["enc.C2"] = C2.T
+    out["tenc.W1"] = umma_image(L1[:, :H])
+    out["tenc.M2"] = umma_image(C1[:, :H] @ L2)
+    out["tenc.C2"] = umma_image(C2)
     out["enc.c2b"] = cb2
 
     g = "encoder_global."
@@ -125,6 +128,10 @@ def fold_state_dict(sd: Dict[str, torch.Tensor], num_convs: int, num_convs_local
             out[p + "P1e"] = W0[:, H:].T
             out[p + "p1b"] = b0
         out[p + "P2"] = _f64(sd[pre + "layers.1.weight"]).T
+        tp = "t" + p
+        out[tp + "P1h"] = umma_image(W0[:, :H])
+        out[tp + "P1e"] = umma_image(W0[:, H:] @ C2 if merged else W0[:, H:])
+        out[tp + "P2"] = umma_image(_f64(sd[pre + "layers.1.weight"]))
         out[p + "p2b"] = _f64(sd[pre + "layers.1.bias"])
         out[p + "p3w"] = _f64(sd[pre + "layers.2.weight"])[0]
         out[p + "p3b"] = _f64(sd[pre + "layers.2.bias"])
