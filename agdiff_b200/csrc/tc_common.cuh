@@ -87,7 +87,10 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 }
 
 constexpr uint32_t TF32_MASK = 0xFFFFE000u;
-constexpr int COL_D = 0, COL_AHI = 128, COL_ALO = 256, TMEM_COLS = 512;
+// TMEM columns: main accumulator (hi.hi products), activation operand hi / lo, cross-term accumulator (hi.lo + lo.hi).
+// The tensor core accumulates fp32 with truncation; keeping the 2^-11-smaller cross terms out of the main accumulator
+// cuts its truncating steps 3x (they are summed in registers by the epilogue).
+constexpr int COL_D = 0, COL_AHI = 128, COL_ALO = 256, COL_D2 = 384, TMEM_COLS = 512;
 
 }  // namespace tc
 
@@ -103,10 +106,23 @@ __device__ __forceinline__ float ssp_fast(float x, float beta) {
   return (y > 20.0f) ? (y - LN2F) : sp;
 }
 
-// split an fp32 value into the TF32-representable high part and the exact fp32 remainder
+// accumulator chunk = main + cross terms
+__device__ __forceinline__ void tmem_ld16_acc(uint32_t trow, int n0, float (&out)[16]) {
+  uint32_t v[16], w[16];
+  tc::tmem_ld16(trow + tc::COL_D + n0, v);
+  tc::tmem_ld16(trow + tc::COL_D2 + n0, w);
+  tc::wait_ld();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) out[j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+}
+
+// split an fp32 value into two TF32 values with round-to-nearest: hi = rna(v), lo = rna(v - hi) (v - hi is exact).
+// |v - (hi + lo)| <= 2^-22 |v| and unbiased; feeding raw fp32 bits instead would let the tensor core TRUNCATE
+// (2^-20, biased), which the far-geometry parity case does not tolerate.
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(v) & tc::TF32_MASK;
-  lo = __float_as_uint(v - __uint_as_float(hi));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+  const float rem = v - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rem));
 }
 
 }  // namespace agd

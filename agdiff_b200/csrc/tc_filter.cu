@@ -3,8 +3,8 @@
 //   W_e = ( F2 . SSP_beta( F1 . g2_e + b1 ) + b2 ) * cw_e          (schnet.py:136-151, merged as in pack.py)
 //
 // fp32 fidelity on tensor cores: plain TF32 fails the 1e-4 parity bar, so every
-// GEMM is 3xTF32:  A.B ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi  with x_hi = x & 0xffffe000 (what the tensor
-// core reads anyway) and x_lo = x - x_hi (exact in fp32), accumulated in fp32 in TMEM.
+// GEMM is 3xTF32:  A.B ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi  with x_hi = rna_tf32(x) and x_lo = rna_tf32(x - x_hi)
+// (round-to-nearest on both parts: 2^-22 relative, unbiased), accumulated in fp32 in TMEM.
 //
 // Data flow of one 128-edge tile (one CTA per SM, 512 threads, 512 TMEM columns):
 //   * the activation operand lives in TENSOR MEMORY (tcgen05.mma with A from TMEM): thread (warp w, lane l) owns
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
       const uint64_t dh = smem_desc_sw128(b_hi + boff), dl = smem_desc_sw128(b_lo + boff);
       const uint32_t a_hi = tmem + COL_AHI + kb * 8, a_lo = tmem + COL_ALO + kb * 8;
       mma_tf32_ts(tmem + COL_D, a_hi, dh, idesc, kb > 0 ? 1u : 0u);
-      mma_tf32_ts(tmem + COL_D, a_hi, dl, idesc, 1u);
-      mma_tf32_ts(tmem + COL_D, a_lo, dh, idesc, 1u);
+      mma_tf32_ts(tmem + COL_D2, a_hi, dl, idesc, kb > 0 ? 1u : 0u);
+      mma_tf32_ts(tmem + COL_D2, a_lo, dh, idesc, 1u);
     }
     mma_commit(&bars[1]);
   };
@@ -135,9 +135,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
         const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t h = __float_as_uint(vv[j]) & TF32_MASK;
-          hi[q * 4 + j] = h;
-          lo[q * 4 + j] = __float_as_uint(vv[j] - __uint_as_float(h));
+          split_tf32(vv[j], hi[q * 4 + j], lo[q * 4 + j]);
         }
       }
       tmem_st16(trow + COL_AHI + part * 32 + c * 16, hi);
@@ -161,16 +159,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
     // ---- epilogue 1: t = SSP_beta(D + b1) -> A (hi/lo) for layer 2
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
-      uint32_t v[16], hi[16], lo[16];
+      uint32_t hi[16], lo[16];
+      float v[16];
       const int n0 = part * PART_COLS + c * 16;
-      tmem_ld16(trow + COL_D + n0, v);
-      wait_ld();
+      tmem_ld16_acc(trow, n0, v);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float t = ssp_fast(__uint_as_float(v[j]) + s_b1[n0 + j], beta);
-        const uint32_t h = __float_as_uint(t) & TF32_MASK;
-        hi[j] = h;
-        lo[j] = __float_as_uint(t - __uint_as_float(h));
+        const float t = ssp_fast(v[j] + s_b1[n0 + j], beta);
+        split_tf32(t, hi[j], lo[j]);
       }
       tmem_st16(trow + COL_AHI + n0, hi);
       tmem_st16(trow + COL_ALO + n0, lo);
@@ -193,19 +189,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
     const float cw = s_cw[my_row];
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
-      uint32_t v[16];
+      float v[16];
       const int n0 = part * PART_COLS + c * 16;
-      tmem_ld16(trow + COL_D + n0, v);
-      wait_ld();
+      tmem_ld16_acc(trow, n0, v);
       if (valid) {
         float4* dst = reinterpret_cast<float4*>(a.filt + r * 192 + a.col0 + n0);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float4 o;
-          o.x = (__uint_as_float(v[q * 4 + 0]) + s_b2[n0 + q * 4 + 0]) * cw;
-          o.y = (__uint_as_float(v[q * 4 + 1]) + s_b2[n0 + q * 4 + 1]) * cw;
-          o.z = (__uint_as_float(v[q * 4 + 2]) + s_b2[n0 + q * 4 + 2]) * cw;
-          o.w = (__uint_as_float(v[q * 4 + 3]) + s_b2[n0 + q * 4 + 3]) * cw;
+          o.x = (v[q * 4 + 0] + s_b2[n0 + q * 4 + 0]) * cw;
+          o.y = (v[q * 4 + 1] + s_b2[n0 + q * 4 + 1]) * cw;
+          o.z = (v[q * 4 + 2] + s_b2[n0 + q * 4 + 2]) * cw;
+          o.w = (v[q * 4 + 3] + s_b2[n0 + q * 4 + 3]) * cw;
           __stcs(dst + q, o);
         }
       }

@@ -35,9 +35,10 @@ struct TcCtx {
       const uint32_t boff = static_cast<uint32_t>(kb >> 2) * (N * 128) + static_cast<uint32_t>(kb & 3) * 32;
       const uint64_t dh = smem_desc_sw128(b_smem + boff), dl = smem_desc_sw128(b_smem + half_bytes + boff);
       const uint32_t a_hi = tmem + COL_AHI + kb * 8, a_lo = tmem + COL_ALO + kb * 8;
-      mma_tf32_ts(tmem + COL_D, a_hi, dh, idesc, (accumulate || kb > 0) ? 1u : 0u);
-      mma_tf32_ts(tmem + COL_D, a_hi, dl, idesc, 1u);
-      mma_tf32_ts(tmem + COL_D, a_lo, dh, idesc, 1u);
+      const uint32_t acc = (accumulate || kb > 0) ? 1u : 0u;
+      mma_tf32_ts(tmem + COL_D, a_hi, dh, idesc, acc);
+      mma_tf32_ts(tmem + COL_D2, a_hi, dl, idesc, acc);
+      mma_tf32_ts(tmem + COL_D2, a_lo, dh, idesc, 1u);
     }
     mma_commit(&bars[1]);
   }
@@ -170,20 +171,18 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) tc_encoder_kernel(const TcEncA
     const float* T1 = a.w.T1 + type * HID;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      uint32_t v[16];
-      float t[16];
+      float v[16], t[16];
       const int n0 = part * 32 + c * 16;
-      tmem_ld16(cx.trow + COL_D + n0, v);
       float4 tb[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) tb[q] = __ldg(reinterpret_cast<const float4*>(T1 + n0) + q);
-      wait_ld();
+      tmem_ld16_acc(cx.trow, n0, v);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        t[q * 4 + 0] = gelu_erf(__uint_as_float(v[q * 4 + 0]) + tb[q].x);
-        t[q * 4 + 1] = gelu_erf(__uint_as_float(v[q * 4 + 1]) + tb[q].y);
-        t[q * 4 + 2] = gelu_erf(__uint_as_float(v[q * 4 + 2]) + tb[q].z);
-        t[q * 4 + 3] = gelu_erf(__uint_as_float(v[q * 4 + 3]) + tb[q].w);
+        t[q * 4 + 0] = gelu_erf(v[q * 4 + 0] + tb[q].x);
+        t[q * 4 + 1] = gelu_erf(v[q * 4 + 1] + tb[q].y);
+        t[q * 4 + 2] = gelu_erf(v[q * 4 + 2] + tb[q].z);
+        t[q * 4 + 3] = gelu_erf(v[q * 4 + 3] + tb[q].w);
       }
       store_split16(cx.trow + COL_AHI + n0, cx.trow + COL_ALO + n0, t);
     }
@@ -198,20 +197,18 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) tc_encoder_kernel(const TcEncA
     const float* T2 = a.w.T2 + type * HID;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      uint32_t v[16];
-      float t[16];
+      float v[16], t[16];
       const int n0 = part * 32 + c * 16;
-      tmem_ld16(cx.trow + COL_D + n0, v);
       float4 tb[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) tb[q] = __ldg(reinterpret_cast<const float4*>(T2 + n0) + q);
-      wait_ld();
+      tmem_ld16_acc(cx.trow, n0, v);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        t[q * 4 + 0] = gelu_erf(__uint_as_float(v[q * 4 + 0]) + tb[q].x);
-        t[q * 4 + 1] = gelu_erf(__uint_as_float(v[q * 4 + 1]) + tb[q].y);
-        t[q * 4 + 2] = gelu_erf(__uint_as_float(v[q * 4 + 2]) + tb[q].z);
-        t[q * 4 + 3] = gelu_erf(__uint_as_float(v[q * 4 + 3]) + tb[q].w);
+        t[q * 4 + 0] = gelu_erf(v[q * 4 + 0] + tb[q].x);
+        t[q * 4 + 1] = gelu_erf(v[q * 4 + 1] + tb[q].y);
+        t[q * 4 + 2] = gelu_erf(v[q * 4 + 2] + tb[q].z);
+        t[q * 4 + 3] = gelu_erf(v[q * 4 + 3] + tb[q].w);
       }
       if (LOCAL) {
         store_split16(cx.trow + COL_AHI + n0, cx.trow + COL_ALO + n0, t);
@@ -227,16 +224,15 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) tc_encoder_kernel(const TcEncA
       if (tid == 0 && more) cx.stream(a.tW1, IMG128);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t v[16];
+        float v[16];
         const int n0 = part * 32 + c * 16;
-        tmem_ld16(cx.trow + COL_D + n0, v);
-        wait_ld();
+        tmem_ld16_acc(cx.trow, n0, v);
         if (valid) {
           float4* dst = reinterpret_cast<float4*>(a.out + r * HID + n0);
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            dst[q] = make_float4(__uint_as_float(v[q * 4]) + s_c2b[n0 + q * 4], __uint_as_float(v[q * 4 + 1]) + s_c2b[n0 + q * 4 + 1],
-                                 __uint_as_float(v[q * 4 + 2]) + s_c2b[n0 + q * 4 + 2], __uint_as_float(v[q * 4 + 3]) + s_c2b[n0 + q * 4 + 3]);
+            dst[q] = make_float4(v[q * 4] + s_c2b[n0 + q * 4], v[q * 4 + 1] + s_c2b[n0 + q * 4 + 1],
+                                 v[q * 4 + 2] + s_c2b[n0 + q * 4 + 2], v[q * 4 + 3] + s_c2b[n0 + q * 4 + 3]);
         }
       }
     }
@@ -373,26 +369,23 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) tc_pair_kernel(const TcPairArg
     // ---- r1 = relu(D + b1) -> A
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      uint32_t v[16];
-      float t[16];
+      float v[16], t[16];
       const int n0 = part * 32 + c * 16;
-      tmem_ld16(cx.trow + COL_D + n0, v);
-      wait_ld();
+      tmem_ld16_acc(cx.trow, n0, v);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) t[j] = relu_(__uint_as_float(v[j]) + s_p1b[n0 + j]);
+      for (int j = 0; j < 16; ++j) t[j] = relu_(v[j] + s_p1b[n0 + j]);
       store_split16(cx.trow + COL_AHI + n0, cx.trow + COL_ALO + n0, t);
     }
     cx.layer_resident(smem_u32(w2buf), 128, 64);        // layers.1
     cx.wait_mma();
     // ---- score = layers.2(relu(D + b2)): 16 columns per thread, four quarters combined through smem
     {
-      uint32_t v[16];
+      float v[16];
       const int n0 = part * 16;
-      tmem_ld16(cx.trow + COL_D + n0, v);
-      wait_ld();
+      tmem_ld16_acc(cx.trow, n0, v);
       float acc = 0.f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc = fmaf(relu_(__uint_as_float(v[j]) + s_p2b[n0 + j]), s_p3w[n0 + j], acc);
+      for (int j = 0; j < 16; ++j) acc = fmaf(relu_(v[j] + s_p2b[n0 + j]), s_p3w[n0 + j], acc);
       s_part[part * 128 + my_row] = acc;
     }
     fence_before_sync();

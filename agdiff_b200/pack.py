@@ -39,16 +39,17 @@ def _fold_bn(sd, lin_key, bn_key):
 
 def umma_image(W: np.ndarray) -> np.ndarray:
     """tcgen05 B-operand image of a Linear weight W[N][K] (N = out, K = in, i.e. K-major): fp32 split into
-    TF32-representable hi = w & 0xffffe000 and lo = fl32(w - hi) & 0xffffe000, each laid out as the canonical
+    TF32 values hi = rna(w) and lo = rna(w - hi) (round-to-nearest, like cvt.rna.tf32.f32), each laid out as the canonical
     K-major SWIZZLE_128B shared-memory layout the UMMA descriptor in csrc/tc_filter.cu describes: K in atoms of
     32 floats (128 B rows), per atom N rows of 128 B, 16-byte chunk c of row n stored at chunk c ^ (n % 8).
     Returns [hi image | lo image] as float32 bit patterns."""
     w32 = np.ascontiguousarray(W, dtype=np.float64).astype(np.float32)
     N, K = w32.shape
     assert K % 32 == 0 and N % 8 == 0
-    bits = w32.view(np.uint32)
-    hi = (bits & np.uint32(0xFFFFE000)).view(np.float32)
-    lo = ((w32 - hi).astype(np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    def rna(x):   # cvt.rna.tf32.f32: round the magnitude to 10 mantissa bits, ties away from zero
+        return ((x.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    hi = rna(w32)
+    lo = rna((w32 - hi).astype(np.float32))
     n = np.arange(N)[:, None]
     k = np.arange(K)[None, :]
     off = (k // 32) * (N * 32) + n * 32 + ((((k % 32) // 4) ^ (n % 8)) * 4) + (k % 4)

@@ -44,11 +44,22 @@ def rel_err(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
 
 
-def assert_close(a, b, rtol=1e-4, atol_scale=1e-5, what=""):
-    """|a-b| <= rtol*|b| + atol, atol = atol_scale * max|b| (outputs span 0.1..100)."""
+def fp32_noise(sd, cfg, z, pos, bi, bt, b, ref32, extend_order=False):
+    """max |fp32 reference - fp64 oracle| for (edge_inv_global, edge_inv_local): the reference's OWN rounding
+    noise on this input.  Ill-conditioned inputs (far geometry: pre-activations ~1e3 for outputs ~1) make it
+    exceed 1e-5*max|ref|; a parity bar tighter than the reference's own noise is not meaningful, so the forward
+    tests allow 4x this on top of rtol 1e-4."""
+    from oracle import agdiff_oracle as O
+    with torch.no_grad():
+        o64 = O.forward(O.to_dtype(sd, torch.float64), cfg, z, pos.double(), bi, bt, b, extend_order=extend_order)
+    return (float((ref32[0].double().cpu() - o64[0]).abs().max()), float((ref32[1].double().cpu() - o64[1]).abs().max()))
+
+
+def assert_close(a, b, rtol=1e-4, atol_scale=1e-5, what="", extra_atol=0.0):
+    """|a-b| <= rtol*|b| + atol, atol = atol_scale * max|b| (outputs span 0.1..100) + extra_atol."""
     a, b = a.double().cpu().reshape(-1), b.double().cpu().reshape(-1)
     assert a.shape == b.shape, "%s: shape %s vs %s" % (what, tuple(a.shape), tuple(b.shape))
-    atol = atol_scale * float(b.abs().max().clamp(min=1e-30))
+    atol = atol_scale * float(b.abs().max().clamp(min=1e-30)) + extra_atol
     bad = (a - b).abs() > (atol + rtol * b.abs())
     assert not bool(bad.any()), "%s: %d/%d elements off, max abs err %.3e (max|ref| %.3e)" % (
         what, int(bad.sum()), a.numel(), float((a - b).abs().max()), float(b.abs().max()))
