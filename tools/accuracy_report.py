@@ -1,0 +1,42 @@
+"""Error of the CUDA forward vs the fp32 reference (golden) and vs the fp64 oracle, for the tensor-core
+(3xTF32 tcgen05) and the fp32 FFMA kernel paths.  Evidence for DESIGN.md section 5; run on a GPU box."""
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import agdiff_oracle as O
+from util import CONFIGS, golden, make_model, state_dict_cpu
+
+CASES = ["fwd_alanine2_qm9", "fwd_alanine2_far_qm9", "fwd_qm9x6_perturbed", "fwd_drugs_mixed_smooth_perturbed",
+         "fwd_drugs_mixed_far_smooth"]
+
+if len(sys.argv) > 1 and sys.argv[1] == "child":
+    for name in CASES:
+        g = golden(name)
+        m = make_model(g["cfg_name"], g["seed"], g["perturb"])
+        sd = state_dict_cpu(m)
+        m = m.to("cuda:0")
+        d = "cuda:0"
+        out = m(g["atom_type"].to(d), g["pos"].to(d), g["bond_index"].to(d), g["bond_type"].to(d), g["batch"].to(d), None,
+                return_edges=True, extend_order=False)
+        with torch.no_grad():
+            o64 = O.forward(O.to_dtype(sd, torch.float64), CONFIGS[g["cfg_name"]], g["atom_type"], g["pos"].double(),
+                            g["bond_index"], g["bond_type"], g["batch"], extend_order=False)
+        row = [name]
+        for k, key in ((0, "edge_inv_global"), (1, "edge_inv_local")):
+            ours, r32, r64 = out[k].double().cpu(), g[key].double(), o64[k]
+            s = float(r64.abs().max())
+            row.append("%s: ours-ref32 %.1e  ours-fp64 %.1e  ref32-fp64 %.1e (max|ref| %.2f)" % (
+                key.split("_")[-1], float((ours - r32).abs().max()) / s, float((ours - r64).abs().max()) / s,
+                float((r32 - r64).abs().max()) / s, s))
+        print(" | ".join(row))
+else:
+    for tc in ("1", "0"):
+        print("== AGD_TC_FILTERS=%s (%s)" % (tc, "tcgen05 3xTF32" if tc == "1" else "fp32 FFMA"))
+        env = dict(os.environ, AGD_TC_FILTERS=tc)
+        subprocess.run([sys.executable, __file__, "child"], env=env, check=True)
