@@ -17,6 +17,7 @@ void set_schnet_attributes();
 void set_gin_attributes();
 void set_tc_attributes();
 void set_tc_mlp_attributes();
+void set_tc_node_attributes();
 }  // namespace agd
 
 using namespace agd;
@@ -95,6 +96,10 @@ static void build_slots(agd_handle* h) {
     add(p + "sc", 4, &b.sc);
     add(p + "tF1a", 2 * 128 * 128, &b.tF1a); add(p + "tF2a", 2 * 128 * 128, &b.tF2a);
     add(p + "tF1b", 2 * 64 * 128, &b.tF1b);   add(p + "tF2b", 2 * 64 * 64, &b.tF2b);
+    add(p + "tL1a", 2 * 128 * 128, &b.tL1a); add(p + "tL1b", 2 * 64 * 128, &b.tL1b);
+    add(p + "tL2a", 2 * 128 * 128, &b.tL2a); add(p + "tL2b", 2 * 128 * 64, &b.tL2b);
+    add(p + "tLINa", 2 * 128 * 128, &b.tLINa); add(p + "tLINb", 2 * 128 * 128, &b.tLINb);
+    add(p + "tA1", 2 * 64 * 128, &b.tA1);
   }
   auto add_pair = [&](const std::string& p, PairW& q) {
     add(p + "P1h", H * H, &q.P1h); add(p + "P1e", H * H, &q.P1e); add(p + "p1b", H, &q.p1b);
@@ -160,11 +165,11 @@ static void run_local_branch(const LaunchCtx& c, const BatchDev& b, const ModelW
 static void run_global_branch(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos) {
   launch_build_edges(c, b, pos);
   if (c.use_tc) launch_encoder_global_tc(c, b, w); else launch_encoder_global(c, b, w);
-  launch_schnet_node(c, b, w, -1);
+  if (c.use_tc) launch_schnet_node_tc(c, b, w, -1); else launch_schnet_node(c, b, w, -1);
   for (int k = 0; k < c.num_convs; ++k) {
     launch_filters(c, b, w, k);
     launch_aggregate(c, b.xcat, b.filt, b.e_src, b.in_ptr, b.n_atoms, 192, b.agg);
-    launch_schnet_node(c, b, w, k);
+    if (c.use_tc) launch_schnet_node_tc(c, b, w, k); else launch_schnet_node(c, b, w, k);
   }
   if (c.use_tc) launch_pair_global_tc(c, b, w); else launch_pair_global(c, b, w);
 }
@@ -198,6 +203,7 @@ int agd_create(const agd_config* cfg, agd_handle** out) {
   set_gin_attributes();
   set_tc_attributes();
   set_tc_mlp_attributes();
+  set_tc_node_attributes();
   if (const char* e = std::getenv("AGD_TC_FILTERS")) h->use_tc = (e[0] != '0');
   CUDA_TRY(cudaGetLastError());
   *out = h;

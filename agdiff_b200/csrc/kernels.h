@@ -32,6 +32,7 @@ struct BlkW {              // InteractionBlock k, schnet.py:165-216 (+ scaling m
   const float *S1, *S2;                      // scaling fc: [128][8], [8][128]
   const float *sc;                           // scalars: beta(conv1.nn.1), beta(conv2.nn.1), beta(act), attention.2.bias
   const float *tF1a, *tF2a, *tF1b, *tF2b;    // tcgen05 operand images of the filter nets: [hi | lo], K-major SWIZZLE_128B
+  const float *tL1a, *tL1b, *tL2a, *tL2b, *tLINa, *tLINb, *tA1;   // ... of the node-side Linears
 };
 struct PairW {             // grad_{global,local}_dist_mlp, common.py:86-103 on [h_row*h_col, edge_attr]
   const float *P1h, *P1e, *p1b;   // layers.0 split: [128][128] on h_row*h_col, [128][128] on g2 (global, merged) / edge_attr (local)
@@ -134,6 +135,7 @@ void launch_encoder_global_tc(const LaunchCtx& c, const BatchDev& b, const Model
 void launch_encoder_local_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos);
 void launch_pair_global_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w);
 void launch_pair_local_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* h_local);
+void launch_schnet_node_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);   // tc_node.cu
 void launch_aggregate(const LaunchCtx& c, const float* x, const float* W, const int* src, const int* in_ptr, int n_nodes,
                       int F, float* out);
 void launch_schnet_node(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk /* -1: embedding + first lin1 */);

@@ -93,6 +93,7 @@ def fold_state_dict(sd: Dict[str, torch.Tensor], num_convs: int, num_convs_local
             cp = "%sconv%d." % (ip, c)
             W, bb = _fold_bn(sd, cp + "lin1", cp + "norm1")
             out[p + "L1" + tag], out[p + "l1%sb" % tag] = W, bb
+            out[p + "tL1" + tag] = umma_image(W.T)                           # images take W[N=out][K=in]
             w0, b0 = _f64(sd[cp + "nn.0.weight"]), _f64(sd[cp + "nn.0.bias"])
             out[p + "F1" + tag] = (w0 @ C2).T
             out[p + "f1%sb" % tag] = w0 @ cb2 + b0
@@ -108,7 +109,11 @@ def fold_state_dict(sd: Dict[str, torch.Tensor], num_convs: int, num_convs_local
             out[p + "dw%d" % c] = dw
             W, bb = _fold_bn(sd, cp + "lin2", cp + "norm2")
             out[p + "L2" + tag], out[p + "l2%sb" % tag] = W, bb
+            out[p + "tL2" + tag] = umma_image(W.T)
         out[p + "LIN"] = _f64(sd[ip + "lin.weight"]).T
+        out[p + "tLINa"] = umma_image(_f64(sd[ip + "lin.weight"])[:, :128])
+        out[p + "tLINb"] = umma_image(_f64(sd[ip + "lin.weight"])[:, 128:])
+        out[p + "tA1"] = umma_image(_f64(sd[ip + "attention.0.weight"]))
         out[p + "linb"] = _f64(sd[ip + "lin.bias"])
         out[p + "A1"] = _f64(sd[ip + "attention.0.weight"]).T
         out[p + "a1b"] = _f64(sd[ip + "attention.0.bias"])
