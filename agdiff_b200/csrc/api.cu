@@ -115,6 +115,7 @@ static void build_slots(agd_handle* h) {
     add(p + "G1", H * H, &g.G1); add(p + "g1b", H, &g.g1b);
     add(p + "G2", H * H, &g.G2); add(p + "g2b", H, &g.g2b);
     add(p + "sc", 1, &g.sc);
+    add(p + "tG1", 2 * H * H, &g.tG1); add(p + "tG2", 2 * H * H, &g.tG2);
   }
 }
 
@@ -153,7 +154,7 @@ static void run_local_branch(const LaunchCtx& c, const BatchDev& b, const ModelW
   const float* x_in = b.gx0;
   float* x_out = b.gx1;
   for (int k = 0; k < c.num_convs_local; ++k) {
-    launch_gin_layer(c, b, w, k, x_in, x_out);
+    if (c.use_tc) launch_gin_layer_tc(c, b, w, k, x_in, x_out); else launch_gin_layer(c, b, w, k, x_in, x_out);
     const float* t = x_in;
     x_in = x_out;
     x_out = const_cast<float*>(t);

@@ -42,6 +42,7 @@ struct PairW {             // grad_{global,local}_dist_mlp, common.py:86-103 on 
 struct GinW {              // GINEConv + BatchNorm, gin.py:38-69,112-148
   const float *G1, *g1b, *G2, *g2b;   // nn.layers.0, nn.layers.1 with batch_norm folded
   const float* sc;                    // [1 + eps]
+  const float *tG1, *tG2;             // tcgen05 [hi|lo] images
 };
 struct ModelW {
   EncW enc;
@@ -136,6 +137,7 @@ void launch_encoder_local_tc(const LaunchCtx& c, const BatchDev& b, const ModelW
 void launch_pair_global_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w);
 void launch_pair_local_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* h_local);
 void launch_schnet_node_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);   // tc_node.cu
+void launch_gin_layer_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int layer, const float* x_in, float* x_out);
 void launch_aggregate(const LaunchCtx& c, const float* x, const float* W, const int* src, const int* in_ptr, int n_nodes,
                       int F, float* out);
 void launch_schnet_node(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk /* -1: embedding + first lin1 */);

@@ -332,6 +332,163 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_node_kernel(const TcNodeArg
   if (warp == 0) tmem_dealloc(cx.tmem, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------ GIN layer
+// m_i = sum_{e: dst_e = i} relu(x[src_e] + ea_e) + (1 + eps) x_i ;  x' = [relu](BN(Lin(relu(Lin(m))))) + x     gin.py:38-69,112-148
+// The gather is row-per-thread (each thread accumulates 32 columns of its node over the CSC segment, two edges in
+// flight), so 512 threads keep ~16 K loads outstanding instead of one warp walking a node's edges one by one.
+struct TcGinArgs {
+  GinW w;
+  const float *tG1, *tG2;
+  const float* x_in;
+  float* x_out;
+  const float* ea;
+  const int *src, *in_ptr;
+  int n_nodes;
+  int last;
+};
+
+constexpr size_t TC_GIN_SMEM = 1024 + 131072 + 256 * sizeof(float) + 256;
+
+__global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* s_g1b = reinterpret_cast<float*>(base + 131072);
+  float* s_g2b = s_g1b + 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_g2b + 128);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, part = warp >> 2;
+  const int my_row = quad * 32 + lane;
+  const int n_rows = a.n_nodes;
+  const int n_tiles = (n_rows + TM - 1) / TM;
+  if (warp == 0) {
+    tmem_alloc(s_tmem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (tid < 128) {
+    s_g1b[tid] = __ldg(a.w.g1b + tid);
+    s_g2b[tid] = __ldg(a.w.g2b + tid);
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  NodeCtx cx;
+  cx.wbuf = base; cx.bars = bars; cx.tmem = *s_tmem;
+  cx.trow = cx.tmem + (static_cast<uint32_t>(quad * 32) << 16);
+  cx.w_phase = 0; cx.m_phase = 0; cx.tid = tid;
+  const float ope = __ldg(a.w.sc);
+  constexpr uint32_t IMG = 2 * 128 * 128 * 4;
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r = static_cast<int64_t>(tile) * TM + my_row;
+    const bool valid = r < n_rows;
+    if (tid == 0) cx.stream(a.tG1, IMG);
+    float m[32], xs[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) m[k] = 0.f, xs[k] = 0.f;
+    if (valid) {
+      const float4* px = reinterpret_cast<const float4*>(a.x_in + r * HID + part * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = __ldg(px + q);
+        xs[q * 4] = v.x; xs[q * 4 + 1] = v.y; xs[q * 4 + 2] = v.z; xs[q * 4 + 3] = v.w;
+      }
+      const int e0 = __ldg(a.in_ptr + r), e1 = __ldg(a.in_ptr + r + 1);
+      int e = e0;
+      for (; e + 2 <= e1; e += 2) {
+        const float4* pa = reinterpret_cast<const float4*>(a.x_in + (size_t)__ldg(a.src + e) * HID + part * 32);
+        const float4* pb = reinterpret_cast<const float4*>(a.x_in + (size_t)__ldg(a.src + e + 1) * HID + part * 32);
+        const float4* ea0 = reinterpret_cast<const float4*>(a.ea + (size_t)e * HID + part * 32);
+        const float4* ea1 = reinterpret_cast<const float4*>(a.ea + (size_t)(e + 1) * HID + part * 32);
+        float4 va[8], vb[8], wa[8], wb[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { va[q] = __ldg(pa + q); wa[q] = __ldg(ea0 + q); vb[q] = __ldg(pb + q); wb[q] = __ldg(ea1 + q); }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          m[q * 4] += relu_(va[q].x + wa[q].x); m[q * 4 + 1] += relu_(va[q].y + wa[q].y);
+          m[q * 4 + 2] += relu_(va[q].z + wa[q].z); m[q * 4 + 3] += relu_(va[q].w + wa[q].w);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          m[q * 4] += relu_(vb[q].x + wb[q].x); m[q * 4 + 1] += relu_(vb[q].y + wb[q].y);
+          m[q * 4 + 2] += relu_(vb[q].z + wb[q].z); m[q * 4 + 3] += relu_(vb[q].w + wb[q].w);
+        }
+      }
+      if (e < e1) {
+        const float4* pa = reinterpret_cast<const float4*>(a.x_in + (size_t)__ldg(a.src + e) * HID + part * 32);
+        const float4* ea0 = reinterpret_cast<const float4*>(a.ea + (size_t)e * HID + part * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v = __ldg(pa + q), w = __ldg(ea0 + q);
+          m[q * 4] += relu_(v.x + w.x); m[q * 4 + 1] += relu_(v.y + w.y); m[q * 4 + 2] += relu_(v.z + w.z); m[q * 4 + 3] += relu_(v.w + w.w);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float t[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t[j] = fmaf(ope, xs[c * 16 + j], m[c * 16 + j]);
+      st_split16(cx.trow, part * 32 + c * 16, t);
+    }
+    cx.layer(128, 128);
+    if (tid == 0) cx.stream(a.tG2, IMG);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float v[16], t[16];
+      const int n0 = part * 32 + c * 16;
+      tmem_ld16_acc(cx.trow, n0, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t[j] = relu_(v[j] + s_g1b[n0 + j]);
+      st_split16(cx.trow, n0, t);
+    }
+    cx.layer(128, 128);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float v[16];
+      const int n0 = part * 32 + c * 16;
+      tmem_ld16_acc(cx.trow, n0, v);
+      if (valid) {
+        float4* dst = reinterpret_cast<float4*>(a.x_out + r * HID + n0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float o[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float t = v[q * 4 + u] + s_g2b[n0 + q * 4 + u];
+            if (!a.last) t = relu_(t);
+            o[u] = t + xs[c * 16 + q * 4 + u];
+          }
+          dst[q] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(cx.tmem, TMEM_COLS);
+}
+
+void launch_gin_layer_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int layer, const float* x_in, float* x_out) {
+  TcGinArgs a{};
+  a.w = w.gin[layer];
+  a.tG1 = w.gin[layer].tG1; a.tG2 = w.gin[layer].tG2;
+  a.x_in = x_in; a.x_out = x_out; a.ea = b.ea_loc; a.src = b.lc_src; a.in_ptr = b.lc_in_ptr;
+  a.n_nodes = b.n_atoms;
+  a.last = (layer == c.num_convs_local - 1) ? 1 : 0;
+  int tiles = (b.n_atoms + TM - 1) / TM;
+  const int grid = tiles < c.num_sms ? tiles : c.num_sms;
+  tc_gin_kernel<<<grid, TCN_THREADS, TC_GIN_SMEM, c.stream>>>(a);
+  note_launch(c, "gin.layer_tc");
+}
+
 void launch_schnet_node_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk) {
   TcNodeArgs a{};
   a.n_nodes = b.n_atoms;
@@ -355,6 +512,7 @@ void launch_schnet_node_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& 
 
 void set_tc_node_attributes() {
   cudaFuncSetAttribute(tc_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_NODE_SMEM);
+  cudaFuncSetAttribute(tc_gin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GIN_SMEM);
 }
 
 }  // namespace agd

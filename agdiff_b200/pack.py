@@ -150,6 +150,8 @@ def fold_state_dict(sd: Dict[str, torch.Tensor], num_convs: int, num_convs_local
         out[p + "g1b"] = _f64(sd["%sconvs.%d.nn.layers.0.bias" % (l, k)])
         W, bb = _fold_bn(sd, "%sconvs.%d.nn.layers.1" % (l, k), "%sbatch_norms.%d" % (l, k))
         out[p + "G2"], out[p + "g2b"] = W, bb
+        out[p + "tG1"] = umma_image(_f64(sd["%sconvs.%d.nn.layers.0.weight" % (l, k)]))
+        out[p + "tG2"] = umma_image(W.T)
         out[p + "sc"] = np.array([1.0 + float(_f64(sd["%sconvs.%d.eps" % (l, k)])[0])])
     return out
 
