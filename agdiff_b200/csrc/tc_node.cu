@@ -347,12 +347,14 @@ struct TcGinArgs {
   int last;
 };
 
-constexpr size_t TC_GIN_SMEM = 1024 + 131072 + 256 * sizeof(float) + 256;
+constexpr int GIN_LD = 132;   // padded row stride of the gathered message tile
+constexpr size_t TC_GIN_SMEM = 1024 + 131072 + (TM * GIN_LD + 256) * sizeof(float) + 256;
 
 __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  float* s_g1b = reinterpret_cast<float*>(base + 131072);
+  float* s_tile = reinterpret_cast<float*>(base + 131072);   // [128][GIN_LD] gathered messages, row-major
+  float* s_g1b = s_tile + TM * GIN_LD;
   float* s_g2b = s_g1b + 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_g2b + 128);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 4);
@@ -388,52 +390,49 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
     const int64_t r = static_cast<int64_t>(tile) * TM + my_row;
     const bool valid = r < n_rows;
     if (tid == 0) cx.stream(a.tG1, IMG);
-    float m[32], xs[32];
+    // ---- gather: one warp per node, lanes across the 128 columns (a row = one coalesced 512 B request), 4 edges in flight
+    const int64_t row0 = static_cast<int64_t>(tile) * TM;
+    for (int rr = warp; rr < TM; rr += TCN_THREADS / 32) {
+      const int64_t node = row0 + rr;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (node < n_rows) {
+        const float4 self = __ldg(reinterpret_cast<const float4*>(a.x_in + node * HID) + lane);
+        const int e0 = __ldg(a.in_ptr + node), e1 = __ldg(a.in_ptr + node + 1);
+        int e = e0;
+        for (; e + 4 <= e1; e += 4) {
+          float4 xv[4], ev[4];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) m[k] = 0.f, xs[k] = 0.f;
-    if (valid) {
-      const float4* px = reinterpret_cast<const float4*>(a.x_in + r * HID + part * 32);
+          for (int u = 0; u < 4; ++u) {
+            xv[u] = __ldg(reinterpret_cast<const float4*>(a.x_in + (size_t)__ldg(a.src + e + u) * HID) + lane);
+            ev[u] = __ldcs(reinterpret_cast<const float4*>(a.ea + (size_t)(e + u) * HID) + lane);
+          }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 v = __ldg(px + q);
-        xs[q * 4] = v.x; xs[q * 4 + 1] = v.y; xs[q * 4 + 2] = v.z; xs[q * 4 + 3] = v.w;
-      }
-      const int e0 = __ldg(a.in_ptr + r), e1 = __ldg(a.in_ptr + r + 1);
-      int e = e0;
-      for (; e + 2 <= e1; e += 2) {
-        const float4* pa = reinterpret_cast<const float4*>(a.x_in + (size_t)__ldg(a.src + e) * HID + part * 32);
-        const float4* pb = reinterpret_cast<const float4*>(a.x_in + (size_t)__ldg(a.src + e + 1) * HID + part * 32);
-        const float4* ea0 = reinterpret_cast<const float4*>(a.ea + (size_t)e * HID + part * 32);
-        const float4* ea1 = reinterpret_cast<const float4*>(a.ea + (size_t)(e + 1) * HID + part * 32);
-        float4 va[8], vb[8], wa[8], wb[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { va[q] = __ldg(pa + q); wa[q] = __ldg(ea0 + q); vb[q] = __ldg(pb + q); wb[q] = __ldg(ea1 + q); }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          m[q * 4] += relu_(va[q].x + wa[q].x); m[q * 4 + 1] += relu_(va[q].y + wa[q].y);
-          m[q * 4 + 2] += relu_(va[q].z + wa[q].z); m[q * 4 + 3] += relu_(va[q].w + wa[q].w);
+          for (int u = 0; u < 4; ++u) {
+            acc.x += relu_(xv[u].x + ev[u].x); acc.y += relu_(xv[u].y + ev[u].y);
+            acc.z += relu_(xv[u].z + ev[u].z); acc.w += relu_(xv[u].w + ev[u].w);
+          }
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          m[q * 4] += relu_(vb[q].x + wb[q].x); m[q * 4 + 1] += relu_(vb[q].y + wb[q].y);
-          m[q * 4 + 2] += relu_(vb[q].z + wb[q].z); m[q * 4 + 3] += relu_(vb[q].w + wb[q].w);
+        for (; e < e1; ++e) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(a.x_in + (size_t)__ldg(a.src + e) * HID) + lane);
+          const float4 ev = __ldcs(reinterpret_cast<const float4*>(a.ea + (size_t)e * HID) + lane);
+          acc.x += relu_(xv.x + ev.x); acc.y += relu_(xv.y + ev.y); acc.z += relu_(xv.z + ev.z); acc.w += relu_(xv.w + ev.w);
         }
+        acc.x = fmaf(ope, self.x, acc.x); acc.y = fmaf(ope, self.y, acc.y);
+        acc.z = fmaf(ope, self.z, acc.z); acc.w = fmaf(ope, self.w, acc.w);
       }
-      if (e < e1) {
-        const float4* pa = reinterpret_cast<const float4*>(a.x_in + (size_t)__ldg(a.src + e) * HID + part * 32);
-        const float4* ea0 = reinterpret_cast<const float4*>(a.ea + (size_t)e * HID + part * 32);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 v = __ldg(pa + q), w = __ldg(ea0 + q);
-          m[q * 4] += relu_(v.x + w.x); m[q * 4 + 1] += relu_(v.y + w.y); m[q * 4 + 2] += relu_(v.z + w.z); m[q * 4 + 3] += relu_(v.w + w.w);
-        }
-      }
+      *reinterpret_cast<float4*>(s_tile + rr * GIN_LD + lane * 4) = acc;
     }
+    __syncthreads();
+    // ---- each thread lifts its row quarter into TMEM
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       float t[16];
+      const float4* ps = reinterpret_cast<const float4*>(s_tile + my_row * GIN_LD + part * 32 + c * 16);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) t[j] = fmaf(ope, xs[c * 16 + j], m[c * 16 + j]);
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = ps[q];
+        t[q * 4] = v.x; t[q * 4 + 1] = v.y; t[q * 4 + 2] = v.z; t[q * 4 + 3] = v.w;
+      }
       st_split16(cx.trow, part * 32 + c * 16, t);
     }
     cx.layer(128, 128);
@@ -455,14 +454,17 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
       tmem_ld16_acc(cx.trow, n0, v);
       if (valid) {
         float4* dst = reinterpret_cast<float4*>(a.x_out + r * HID + n0);
+        const float4* pxo = reinterpret_cast<const float4*>(a.x_in + r * HID + n0);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+          const float4 xq = __ldg(pxo + q);
+          const float xo[4] = {xq.x, xq.y, xq.z, xq.w};
           float o[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             float t = v[q * 4 + u] + s_g2b[n0 + q * 4 + u];
             if (!a.last) t = relu_(t);
-            o[u] = t + xs[c * 16 + q * 4 + u];
+            o[u] = t + xo[u];
           }
           dst[q] = make_float4(o[0], o[1], o[2], o[3]);
         }
