@@ -116,6 +116,26 @@ __device__ __forceinline__ void tmem_ld16_acc(uint32_t trow, int n0, float (&out
   for (int j = 0; j < 16; ++j) out[j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
 }
 
+// single accumulator variant (kernels whose outputs are averaged downstream: filter nets, edge encoder)
+__device__ __forceinline__ void tmem_ld16_main(uint32_t trow, int n0, float (&out)[16]) {
+  uint32_t v[16];
+  tc::tmem_ld16(trow + tc::COL_D + n0, v);
+  tc::wait_ld();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) out[j] = __uint_as_float(v[j]);
+}
+__device__ __forceinline__ void tmem_ld32_main(uint32_t trow, int n0, float (&out)[32]) {
+  uint32_t v[16], w[16];
+  tc::tmem_ld16(trow + tc::COL_D + n0, v);
+  tc::tmem_ld16(trow + tc::COL_D + n0 + 16, w);
+  tc::wait_ld();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    out[j] = __uint_as_float(v[j]);
+    out[16 + j] = __uint_as_float(w[j]);
+  }
+}
+
 // split an fp32 value into two TF32 values with round-to-nearest: hi = rna(v), lo = rna(v - hi) (v - hi is exact).
 // |v - (hi + lo)| <= 2^-22 |v| and unbiased; feeding raw fp32 bits instead would let the tensor core TRUNCATE
 // (2^-20, biased), which the far-geometry parity case does not tolerate.
