@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--regime", default="compact", choices=["compact", "random_init"])
     ap.add_argument("--workload", default="drugs", choices=["drugs", "qm9"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--cpu-steps", type=int, default=200, help="oracle steps timed per CPU sample (~10 s of CPU work)")
     return ap.parse_args()
 
 

@@ -351,3 +351,51 @@ def test_op_eq_transform():
     _lib.check(lib.agd_op_eq_transform(*[C.c_void_p(t.data_ptr()) for t in a], E, N, C.c_void_p(out.data_ptr()), st))
     torch.cuda.synchronize()
     assert_close(out, ref, rtol=1e-4, atol_scale=1e-5, what="eq_transform")
+
+
+# ------------------------------------------------------------------------------- full-size properties
+def test_full_size_batch_properties():
+    """BASELINE-sized batch (1024 QM9-shaped molecules x 2 / 300 Drugs-shaped incl. 181 atoms): properties that do not
+    need the CPU oracle -- canonical order, no self loops, in-degree cap, local edges == static edges, symmetric local
+    scores, permutation equivariance over molecules, translation invariance."""
+    for cfg_name, mols in (("qm9", synth.qm9_like(1024, seed=2021)), ("drugs", synth.drugs_like(300, seed=2021))):
+        m, sd = _cuda_model(cfg_name, 2021, 3)
+        _settle(m)
+        ext = [graph.extend_bond_order_host(x) for x in mols]
+        z, bi, bt, b, G = graph.collate(ext, 2)
+        N = z.numel()
+        pos = torch.randn(N, 3, generator=torch.Generator().manual_seed(1)) * 2.0
+        d = [t.to(DEV) for t in (z, pos, bi, bt, b)]
+        eg, el, ei, et, elen, mask = m(d[0], d[1], d[2], d[3], d[4], None, return_edges=True, extend_order=False)
+        key = ei[0] * N + ei[1]
+        assert bool((key[1:] > key[:-1]).all()), "edge list not in canonical (row*N+col) order / has duplicates"
+        assert bool((ei[0] != ei[1]).all()) and bool((b.to(DEV)[ei[0]] == b.to(DEV)[ei[1]]).all())
+        indeg = torch.bincount(ei[1], minlength=N)
+        st_in = torch.bincount(bi[1], minlength=N).to(DEV)
+        assert int((indeg - st_in).max()) <= 33                                 # radius_graph keeps at most 32 (+1) per query
+        assert torch.equal(ei[:, mask].cpu(), bi) and torch.equal(et[mask].cpu(), bt)     # local edges are exactly the static ones
+        assert bool(torch.isfinite(eg).all()) and bool(torch.isfinite(el).all())
+        assert float((elen.view(-1) - (d[1][ei[0]] - d[1][ei[1]]).norm(dim=-1)).abs().max()) < 1e-5
+        # the local graph is symmetric and so are its scores: s(a,b) == s(b,a) bitwise (same inputs, same arithmetic)
+        li = ei[:, mask]
+        rev = torch.argsort(li[1] * N + li[0])
+        assert torch.equal(li[:, rev].flip(0), li) and torch.equal(el[rev], el)
+        # translation invariance (per-molecule shift) within fp32 rounding of the distances
+        shift = torch.randn(G, 3, generator=torch.Generator().manual_seed(2))[b].to(DEV)
+        eg2, el2 = m(d[0], d[1] + shift, d[2], d[3], d[4], None, extend_order=False)
+        assert eg2.shape == eg.shape
+        assert float((el2 - el).abs().max()) <= 2e-3 * float(el.abs().max())
+        # reversing the molecule order permutes the outputs and nothing else (tiles are composed differently)
+        order = list(range(len(ext)))[::-1]
+        z2, bi2, bt2, b2, _ = graph.collate([ext[i] for i in order], 2)
+        sizes = torch.tensor([x.num_nodes for x in ext]).repeat_interleave(2)
+        starts = torch.cumsum(sizes, 0) - sizes
+        conf_order = [2 * i + s for i in order for s in range(2)]
+        perm = torch.cat([torch.arange(int(starts[c]), int(starts[c] + sizes[c])) for c in conf_order])
+        out2 = m(z2.to(DEV), pos[perm].to(DEV), bi2.to(DEV), bt2.to(DEV), b2.to(DEV), None, return_edges=True, extend_order=False)
+        inv = torch.empty(N, dtype=torch.long)
+        inv[perm] = torch.arange(N)
+        ei_back = perm.to(DEV)[out2[2]]                       # edges of the permuted batch, in original atom numbering
+        k2 = ei_back[0] * N + ei_back[1]
+        o = torch.argsort(k2)
+        assert torch.equal(k2[o], key) and torch.equal(out2[0][o], eg), "outputs depend on batch composition"

@@ -1,0 +1,71 @@
+"""BASELINE.json config 4: gather/scatter microbenchmarks over an edge-count sweep.
+
+Synthetic CSR graphs, in-degree 32, N = E/32, uniform features in [-1, 1], seed 0:
+  (i)  CFConv message + aggregate, F in {128, 64, 192}: agg_i = sum_e x[src_e] * W_e        (agd_op_cfconv_aggregate)
+  (iii) eq_transform: out[row] += dd*s, out[col] -= dd*s                                    (agd_op_eq_transform)
+Prints achieved GB/s with the algorithmic bytes of SURVEY 8d (indices as int32) against MEASURED_PEAKS.json.
+Each timing: 3 warm-up + 10 timed launches with CUDA events; inputs are larger than L2 from E >= 3e5 (F=128).
+"""
+import ctypes as C
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from agdiff_b200 import _lib
+
+lib = _lib.load()
+dev = "cuda:0"
+peak = 6650.0
+try:
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+P = lambda t: C.c_void_p(t.data_ptr())
+
+
+def timeit(fn, reps=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+rows = []
+gen = torch.Generator().manual_seed(0)
+for E in (100_000, 300_000, 1_000_000, 3_000_000, 10_000_000):
+    N = E // 32
+    E = N * 32
+    src = torch.randint(0, N, (E,), generator=gen).to(torch.int32).to(dev)
+    in_ptr = (torch.arange(N + 1, dtype=torch.int32) * 32).to(dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for F in (128, 64, 192):
+        x = (torch.rand(N, F, generator=gen) * 2 - 1).to(dev)
+        W = (torch.rand(E, F, generator=gen) * 2 - 1).to(dev)
+        out = torch.empty(N, F, device=dev)
+        t = timeit(lambda: _lib.check(lib.agd_op_cfconv_aggregate(P(x), P(W), P(src), P(in_ptr), N, F, P(out), st)))
+        byts = E * (4 * F + 4 * F + 4) + N * (4 * F + 4)
+        rows.append(("cfconv_aggregate F=%d" % F, E, t * 1e6, byts / t / 1e9))
+        del x, W, out
+    pos = torch.randn(N, 3, generator=gen).to(dev)
+    dst = torch.arange(N, dtype=torch.int32).repeat_interleave(32).to(dev)
+    ln = (torch.rand(E, generator=gen) + 0.5).to(dev)
+    sc = torch.randn(E, generator=gen).to(dev)
+    out = torch.empty(N, 3, device=dev)
+    t = timeit(lambda: _lib.check(lib.agd_op_eq_transform(P(sc), P(pos), P(src), P(dst), P(ln), E, N, P(out), st)))
+    byts = E * (4 + 8 + 4 + 24) + N * 24
+    rows.append(("eq_transform (atomics)", E, t * 1e6, byts / t / 1e9))
+
+print("| kernel | edges | us/launch | algorithmic GB/s | frac of measured HBM peak (%.0f GB/s) |" % peak)
+print("|---|---|---|---|---|")
+for name, E, us, gbs in rows:
+    print("| %s | %d | %.1f | %.0f | %.2f |" % (name, E, us, gbs, gbs / peak))
