@@ -99,7 +99,8 @@ constexpr int COL_D = 0, COL_AHI = 128, COL_ALO = 256, COL_D2 = 384, TMEM_COLS =
 // value feeds a 128-term fp32 dot product).  Matches F.softplus' threshold-20 branch.
 __device__ __forceinline__ float ssp_fast(float x, float beta) {
   const float y = beta * x;
-  const float e = exp2f(y * 1.4426950408889634f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y * 1.4426950408889634f));
   float sp;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(sp) : "f"(1.0f + e));
   sp = fmaf(sp, LN2F, -LN2F);

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
   constexpr int PART_COLS = F / 4;                     // output columns owned by one of the 4 warp groups
   constexpr int CHUNKS = PART_COLS / 16;               // 2 (F=128) or 1 (F=64)
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer (LDS, not generic LD)
   uint8_t* wbuf = base;                                             // 128 KB, 1024-aligned
   float* s_cw = reinterpret_cast<float*>(base + 131072);            // [128] envelope weight of each tile row
   float* s_b1 = s_cw + 128;                                         // [F] layer-1 bias

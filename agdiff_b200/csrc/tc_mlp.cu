@@ -99,7 +99,7 @@ constexpr size_t TC_ENC_SMEM = 1024 + 131072 + 4 * 128 * sizeof(float) + 256;
 template <bool LOCAL>
 __global__ void __launch_bounds__(TCM_THREADS, 1) tc_encoder_kernel(const TcEncArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer (LDS, not generic LD)
   float* s_few = reinterpret_cast<float*>(base + 131072);   // feature_expansion weight
   float* s_feb = s_few + 128;                               // feature_expansion bias
   float* s_c2b = s_feb + 128;
@@ -262,7 +262,7 @@ constexpr size_t TC_PAIR_SMEM = 1024 + 131072 + 65536 + (128 + 64 + 64 + 4 * 128
 
 __global__ void __launch_bounds__(TCM_THREADS, 1) tc_pair_kernel(const TcPairArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer (LDS, not generic LD)
   uint8_t* w2buf = base + 131072;                              // resident 128->64 layer, 64 KB
   float* s_p1b = reinterpret_cast<float*>(base + 131072 + 65536);
   float* s_p2b = s_p1b + 128;

@@ -80,7 +80,7 @@ __device__ __forceinline__ void st_split16(uint32_t trow, int k0, const float (&
 
 __global__ void __launch_bounds__(TCN_THREADS, 1) tc_node_kernel(const TcNodeArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer (LDS, not generic LD)
   float* s_l2ab = reinterpret_cast<float*>(base + 131072);
   float* s_l2bb = s_l2ab + 128;
   float* s_linb = s_l2bb + 128;
@@ -352,7 +352,7 @@ constexpr size_t TC_GIN_SMEM = 1024 + 131072 + (TM * GIN_LD + 256) * sizeof(floa
 
 __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer (LDS, not generic LD)
   float* s_tile = reinterpret_cast<float*>(base + 131072);   // [128][GIN_LD] gathered messages, row-major
   float* s_g1b = s_tile + TM * GIN_LD;
   float* s_g2b = s_g1b + 128;
