@@ -137,6 +137,28 @@ __device__ __forceinline__ void tmem_ld32_main(uint32_t trow, int n0, float (&ou
   }
 }
 
+// The whole 3xTF32 issue sequence of one layer, D[128 x N] (+)= A[128 x K] . W^T, for ONE thread.  K and N are compile-time
+// so the K/8 x 3 instructions are straight-line code: descriptors are the layer's base descriptor plus a constant (the
+// 14-bit address field cannot carry: shared addresses are < 256 KB), instead of being rebuilt in a serial loop that is
+// itself as long as the tensor core needs to execute the MMAs.  SPLIT: cross terms go to the second accumulator.
+template <int K, int N, bool SPLIT>
+__device__ __forceinline__ void issue_3xtf32(uint32_t tmem, uint32_t b_smem, bool accumulate) {
+  constexpr uint32_t idesc = tc::idesc_tf32(N);
+  constexpr uint32_t half_bytes = static_cast<uint32_t>(K) * N * 4;
+  const uint64_t d_hi = tc::smem_desc_sw128(b_smem), d_lo = tc::smem_desc_sw128(b_smem + half_bytes);
+  const uint32_t dmain = tmem + tc::COL_D, dx = tmem + (SPLIT ? tc::COL_D2 : tc::COL_D);
+#pragma unroll
+  for (int kb = 0; kb < K / 8; ++kb) {
+    const uint32_t boff16 = (static_cast<uint32_t>(kb >> 2) * (N * 128) + static_cast<uint32_t>(kb & 3) * 32) >> 4;
+    const uint64_t dh = d_hi + boff16, dl = d_lo + boff16;
+    const uint32_t a_hi = tmem + tc::COL_AHI + kb * 8, a_lo = tmem + tc::COL_ALO + kb * 8;
+    const uint32_t acc = (accumulate || kb > 0) ? 1u : 0u;
+    tc::mma_tf32_ts(dmain, a_hi, dh, idesc, acc);
+    tc::mma_tf32_ts(dx, a_hi, dl, idesc, SPLIT ? acc : 1u);
+    tc::mma_tf32_ts(dx, a_lo, dh, idesc, 1u);
+  }
+}
+
 // split an fp32 value into two TF32 values with round-to-nearest: hi = rna(v), lo = rna(v - hi) (v - hi is exact).
 // |v - (hi + lo)| <= 2^-22 |v| and unbiased; feeding raw fp32 bits instead would let the tensor core TRUNCATE
 // (2^-20, biased), which the far-geometry parity case does not tolerate.

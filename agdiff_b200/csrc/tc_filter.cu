@@ -38,7 +38,7 @@ struct TcFiltArgs {
 };
 
 constexpr int TC_THREADS = 512;
-constexpr size_t TC_FILT_SMEM = 1024 /*align slack*/ + 131072 /*weights hi|lo*/ + (128 + 128 + 128 + 128) * sizeof(float) + 64;
+constexpr size_t TC_FILT_SMEM = 1024 /*align slack*/ + 131072 /*weights hi|lo*/ + (256 + 128 + 128 + 128) * sizeof(float) + 64;
 
 template <int F>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltArgs a) {
@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer (LDS, not generic LD)
   uint8_t* wbuf = base;                                             // 128 KB, 1024-aligned
-  float* s_cw = reinterpret_cast<float*>(base + 131072);            // [128] envelope weight of each tile row
-  float* s_b1 = s_cw + 128;                                         // [F] layer-1 bias
+  float* s_cw = reinterpret_cast<float*>(base + 131072);            // [2][128] envelope weight of each tile row (double-buffered)
+  float* s_b1 = s_cw + 256;                                         // [F] layer-1 bias
   float* s_b2 = s_b1 + 128;                                         // [F] layer-2 bias
   float* s_dw = s_b2 + 128;                                         // [128] distance-weighting MLP
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_dw + 128);         // [0]=weights landed, [1]=mma done
@@ -97,17 +97,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
     const uint8_t* src = reinterpret_cast<const uint8_t*>(img);
     for (uint32_t off = 0; off < 2 * half_bytes; off += 16384) bulk_g2s(wbuf + off, src + off, 16384, &bars[0]);
   };
-  auto issue_layer = [&](int K, uint32_t half_bytes) {               // tid 0 only
-    const uint32_t idesc = idesc_tf32(F);
-    const uint32_t b_hi = smem_u32(wbuf), b_lo = smem_u32(wbuf) + half_bytes;
-    for (int kb = 0; kb < K / 8; ++kb) {
-      const uint32_t boff = static_cast<uint32_t>(kb >> 2) * (F * 128) + static_cast<uint32_t>(kb & 3) * 32;
-      const uint64_t dh = smem_desc_sw128(b_hi + boff), dl = smem_desc_sw128(b_lo + boff);
-      const uint32_t a_hi = tmem + COL_AHI + kb * 8, a_lo = tmem + COL_ALO + kb * 8;
-      mma_tf32_ts(tmem + COL_D, a_hi, dh, idesc, kb > 0 ? 1u : 0u);   // one accumulator: these outputs are scaled by the
-      mma_tf32_ts(tmem + COL_D, a_hi, dl, idesc, 1u);                 // envelope (<= 1) and summed over ~33 edges downstream,
-      mma_tf32_ts(tmem + COL_D, a_lo, dh, idesc, 1u);                 // measured error stays at the fp32 noise level
-    }
+  // one accumulator (SPLIT=false): these outputs are scaled by the envelope (<= 1) and summed over ~33 edges downstream,
+  // the measured error stays at the fp32 noise level
+  auto issue_layer1 = [&]() {   // tid 0 only
+    issue_3xtf32<HID, F, false>(tmem, smem_u32(wbuf), false);
+    mma_commit(&bars[1]);
+  };
+  auto issue_layer2 = [&]() {
+    issue_3xtf32<F, F, false>(tmem, smem_u32(wbuf), false);
     mma_commit(&bars[1]);
   };
   // this thread's slice of a g2 row: 32 input features = 8 x float4, kept in registers one tile ahead
@@ -130,12 +127,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
   if (tid == 0 && blockIdx.x < n_tiles) load_weights(a.W1img, W1_HALF);
   prefetch(blockIdx.x);
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    float* cwbuf = s_cw + (it & 1) * 128;
     const int64_t row0 = static_cast<int64_t>(tile) * TM;
     const int64_t r = row0 + my_row;
     const bool valid = r < n_rows;
     // ---- stage A = g2 tile (hi/lo) into TMEM from the prefetched registers; envelope weight into smem
-    if (part == 3) s_cw[my_row] = valid ? cfconv_edge_weight_smem(pre_len, s_dw, a.cutoff, a.smooth) : 0.f;
+    if (part == 3) cwbuf[my_row] = valid ? cfconv_edge_weight_smem(pre_len, s_dw, a.cutoff, a.smooth) : 0.f;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t hi[16], lo[16];
@@ -158,7 +157,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
     if (tid == 0) {
       fence_after_sync();
       mbar_wait(&bars[0], w_phase);
-      issue_layer(HID, W1_HALF);
+      issue_layer1();
     }
     w_phase ^= 1;
     prefetch(tile + static_cast<int>(gridDim.x));    // next tile's operand rows travel while the tensor core works
@@ -191,7 +190,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
     if (tid == 0) {
       fence_after_sync();
       mbar_wait(&bars[0], w_phase);
-      issue_layer(F, W2_HALF);
+      issue_layer2();
     }
     w_phase ^= 1;
     mbar_wait(&bars[1], m_phase);
@@ -199,7 +198,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
     fence_after_sync();
     if (tid == 0 && tile + static_cast<int>(gridDim.x) < n_tiles) load_weights(a.W1img, W1_HALF);
     // ---- epilogue 2: W = (D + b2) * cw -> global filt[e][col0 + n]
-    const float cw = s_cw[my_row];
+    const float cw = cwbuf[my_row];
     {
       float v[16 * CHUNKS];
       const int nb = part * PART_COLS;
@@ -217,9 +216,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
         }
       }
     }
-    fence_before_sync();
-    __syncthreads();   // D and s_cw are free for the next tile
-    fence_after_sync();
+    // no barrier here: the next tile's operand stores target the A columns (dead since layer 2 completed), its envelope
+    // weights go to the other s_cw buffer, and D is only overwritten after the next tile's post-staging barrier
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);

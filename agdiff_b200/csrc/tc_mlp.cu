@@ -29,19 +29,11 @@ struct TcCtx {
     for (uint32_t off = 0; off < bytes; off += 16384) bulk_g2s(wbuf + off, src + off, 16384, &bars[0]);
   }
   // D[128 x N] (+)= A[128 x K] . W^T with W's [hi|lo] image at `b_smem` (hi at +0, lo at +half_bytes); tid 0 only
-  bool split_acc;   // true: hi.lo + lo.hi products go to the second accumulator (COL_D2), summed by the epilogue
-  __device__ __forceinline__ void issue(uint32_t b_smem, uint32_t half_bytes, int K, int N, bool accumulate) {
-    const uint32_t idesc = idesc_tf32(N);
-    const uint32_t dx = tmem + (split_acc ? COL_D2 : COL_D);
-    for (int kb = 0; kb < K / 8; ++kb) {
-      const uint32_t boff = static_cast<uint32_t>(kb >> 2) * (N * 128) + static_cast<uint32_t>(kb & 3) * 32;
-      const uint64_t dh = smem_desc_sw128(b_smem + boff), dl = smem_desc_sw128(b_smem + half_bytes + boff);
-      const uint32_t a_hi = tmem + COL_AHI + kb * 8, a_lo = tmem + COL_ALO + kb * 8;
-      const uint32_t acc = (accumulate || kb > 0) ? 1u : 0u;
-      mma_tf32_ts(tmem + COL_D, a_hi, dh, idesc, acc);
-      mma_tf32_ts(dx, a_hi, dl, idesc, split_acc ? acc : 1u);
-      mma_tf32_ts(dx, a_lo, dh, idesc, 1u);
-    }
+  // D[128 x N] (+)= A[128 x K] . W^T with W's [hi|lo] image at `b_smem`; tid 0 only.  Cross terms go to the second accumulator.
+  __device__ __forceinline__ void issue(uint32_t b_smem, uint32_t /*half_bytes*/, int K, int N, bool accumulate) {
+    if (K == 128 && N == 128) issue_3xtf32<128, 128, true>(tmem, b_smem, accumulate);
+    else issue_3xtf32<128, 64, true>(tmem, b_smem, accumulate);   // the only other shape used here
+    (void)K; (void)N;
     mma_commit(&bars[1]);
   }
   // publish this thread's TMEM stores, run one streamed layer, wait for it (all threads call)
@@ -132,7 +124,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) tc_encoder_kernel(const TcEncA
   TcCtx cx;
   cx.wbuf = base; cx.bars = bars; cx.tmem = *s_tmem;
   cx.trow = cx.tmem + (static_cast<uint32_t>(quad * 32) << 16);
-  cx.w_phase = 0; cx.m_phase = 0; cx.tid = tid; cx.split_acc = true;
+  cx.w_phase = 0; cx.m_phase = 0; cx.tid = tid;
 
   if (tid == 0 && blockIdx.x < n_tiles) cx.stream(a.tW1, IMG128);
 
@@ -298,7 +290,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) tc_pair_kernel(const TcPairArg
   TcCtx cx;
   cx.wbuf = base; cx.bars = bars; cx.tmem = *s_tmem;
   cx.trow = cx.tmem + (static_cast<uint32_t>(quad * 32) << 16);
-  cx.w_phase = 0; cx.m_phase = 0; cx.tid = tid; cx.split_acc = true;
+  cx.w_phase = 0; cx.m_phase = 0; cx.tid = tid;
   const float p3b = __ldg(a.w.p3b);
 
   if (tid == 0 && blockIdx.x < n_tiles) {

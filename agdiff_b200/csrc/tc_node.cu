@@ -50,17 +50,10 @@ struct NodeCtx {   // TcCtx from tc_mlp.cu, repeated here to keep the translatio
     if (tid == 0) {
       fence_after_sync();
       mbar_wait(&bars[0], w_phase);
-      const uint32_t idesc = idesc_tf32(N);
-      const uint32_t b_smem = smem_u32(wbuf), half_bytes = static_cast<uint32_t>(K) * N * 4;
-      for (int kb = 0; kb < K / 8; ++kb) {
-        const uint32_t boff = static_cast<uint32_t>(kb >> 2) * (N * 128) + static_cast<uint32_t>(kb & 3) * 32;
-        const uint64_t dh = smem_desc_sw128(b_smem + boff), dl = smem_desc_sw128(b_smem + half_bytes + boff);
-        const uint32_t a_hi = tmem + COL_AHI + kb * 8, a_lo = tmem + COL_ALO + kb * 8;
-        const uint32_t acc = kb > 0 ? 1u : 0u;
-        mma_tf32_ts(tmem + COL_D, a_hi, dh, idesc, acc);
-        mma_tf32_ts(tmem + COL_D2, a_hi, dl, idesc, acc);
-        mma_tf32_ts(tmem + COL_D2, a_lo, dh, idesc, 1u);
-      }
+      const uint32_t b_smem = smem_u32(wbuf);
+      if (K == 128 && N == 128) issue_3xtf32<128, 128, true>(tmem, b_smem, false);
+      else if (K == 64 && N == 128) issue_3xtf32<64, 128, true>(tmem, b_smem, false);
+      else issue_3xtf32<128, 64, true>(tmem, b_smem, false);
       mma_commit(&bars[1]);
     }
     w_phase ^= 1;
