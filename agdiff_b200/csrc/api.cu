@@ -169,7 +169,7 @@ static void run_global_branch(const LaunchCtx& c, const BatchDev& b, const Model
   if (c.use_tc) launch_schnet_node_tc(c, b, w, -1); else launch_schnet_node(c, b, w, -1);
   for (int k = 0; k < c.num_convs; ++k) {
     launch_filters(c, b, w, k);
-    launch_aggregate(c, b.xcat, b.filt, b.e_src, b.in_ptr, b.n_atoms, 192, b.agg);
+    if (!(c.use_tc && filters_tc_fused())) launch_aggregate(c, b.xcat, b.filt, b.e_src, b.in_ptr, b.n_atoms, 192, b.agg);
     if (c.use_tc) launch_schnet_node_tc(c, b, w, k); else launch_schnet_node(c, b, w, k);
   }
   if (c.use_tc) launch_pair_global_tc(c, b, w); else launch_pair_global(c, b, w);

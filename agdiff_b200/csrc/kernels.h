@@ -131,6 +131,7 @@ void launch_pair_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w, c
 // schnet.cu
 void launch_filters(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);
 void launch_filters_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);   // tc_filter.cu
+bool filters_tc_fused();   // true: launch_filters_tc also performs the CFConv aggregation into agg
 // tc_mlp.cu
 void launch_encoder_global_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w);
 void launch_encoder_local_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos);

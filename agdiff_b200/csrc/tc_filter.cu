@@ -1,6 +1,7 @@
-// CFConv filter-generating network on the 5th-generation tensor cores (tcgen05, sm_100a).
+// CFConv on the 5th-generation tensor cores (tcgen05, sm_100a): the filter-generating network, optionally fused with
+// the gather -> multiply -> segmented-sum aggregation (schnet.py:136-162, merged as in pack.py):
 //
-//   W_e = ( F2 . SSP_beta( F1 . g2_e + b1 ) + b2 ) * cw_e          (schnet.py:136-151, merged as in pack.py)
+//   W_e = ( F2 . SSP_beta( F1 . g2_e + b1 ) + b2 ) * cw_e            agg_i = sum_{e: dst_e = i} x[src_e] (.) W_e
 //
 // fp32 fidelity on tensor cores: plain TF32 fails the 1e-4 parity bar, so every
 // GEMM is 3xTF32:  A.B ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi  with x_hi = rna_tf32(x) and x_lo = rna_tf32(x - x_hi)
@@ -17,6 +18,13 @@
 //     are fetched while the layer-1 epilogue runs, the next tile's layer-1 weights during the layer-2 epilogue.
 //   * one elected thread issues the 3 x K/8 tcgen05.mma (M=128, N=F, K=8) per layer and tcgen05.commit's to an
 //     mbarrier that the 512 epilogue threads wait on.
+//   * OPTIONAL FUSED AGGREGATION (AGD_TC_FUSE_AGG=1, off by default - see tc_fuse_default): the layer-2 epilogue leaves the filter tile in shared memory instead of HBM; while the tensor
+//     core runs the NEXT tile's layer 1 the 16 warps reduce it: warp w owns rows 8w..8w+7 (edges are CSC-sorted, so rows
+//     of one destination are consecutive), multiplies by the gathered x[src] rows (coalesced: one row per warp request)
+//     and sums per destination run.  A run that continues from the previous chunk is parked in shared memory and added
+//     by the warp that owns the run's first row, in chunk order, so the sum order is fixed (bit-reproducible); only runs
+//     cut by a TILE boundary use atomicAdd into the zeroed agg row - exactly two commutative contributions.
+//     The 768 B/edge/block filter tensor never reaches HBM and the separate aggregate kernel disappears.
 #include <cstdlib>
 
 #include "kernels.h"
@@ -30,15 +38,139 @@ struct TcFiltArgs {
   const float *f1b, *f2b, *dw, *beta_ptr;
   const int* n_rows_dev;
   const float *g2, *e_len;
-  float* filt;
-  int col0;
+  float* filt;          // [E][192] (only written when !fuse)
+  int col0;             // 0 (conv1) or 128 (conv2): column offset in filt / xcat / agg
   float cutoff;
   int smooth;
-  int debug_nostream;   // timing experiment only: load the weights once, never re-stream (WRONG results)
+  int fuse;             // 1: aggregate in-kernel into agg, 0: write filt for cfconv_aggregate_kernel
+  const float* xcat;    // [N][192] lin1 outputs of the current block
+  float* agg;           // [N][192], zeroed before the launch when fuse
+  const int *e_src, *e_dst;
 };
 
 constexpr int TC_THREADS = 512;
-constexpr size_t TC_FILT_SMEM = 1024 /*align slack*/ + 131072 /*weights hi|lo*/ + (256 + 128 + 128 + 128) * sizeof(float) + 64;
+constexpr int TCF_WARPS = TC_THREADS / 32;
+template <int F>
+struct TcFiltSmem {
+  static constexpr int LDW = F + 4;   // padded row stride of the filter tile
+  static constexpr size_t bytes = 1024 /*align slack*/ + 131072 /*weights hi|lo*/ +
+                                  (256 + 128 + 128 + 128 + TM * LDW + TCF_WARPS * F) * sizeof(float) + 4 * TM * sizeof(int) + 64;
+};
+
+// Deterministic segmented reduction of one filter tile (see header).  All 512 threads call it; contains one barrier.
+template <int F>
+__device__ __forceinline__ void aggregate_tile(const TcFiltArgs& a, const float* s_W, const int* s_src, const int* s_dst, float* s_P,
+                                               int64_t base, int n_valid, int n_rows, int warp, int lane) {
+  constexpr int LDW = TcFiltSmem<F>::LDW;
+  constexpr int VEC = F / 32;   // floats per lane: 4 (F = 128) or 2 (F = 64)
+  const int R0 = warp * 8;
+  const int c0 = VEC * lane;
+  auto row_dst = [&](int row) { return (row < n_valid) ? s_dst[row] : -1; };
+  // destination of the row just before this chunk (previous chunk, or the previous tile's last row)
+  int prev_dst = -2;
+  if (R0 > 0) prev_dst = row_dst(R0 - 1);
+  else if (base > 0) prev_dst = __ldg(a.e_dst + base - 1);
+  auto write_out = [&](int dst, const float (&v)[VEC], bool boundary) {
+    float* o = a.agg + (size_t)dst * 192 + a.col0 + c0;
+    if (boundary) {
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) atomicAdd(o + u, v[u]);
+    } else if (VEC == 4) {
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      *reinterpret_cast<float2*>(o) = make_float2(v[0], v[1]);
+    }
+  };
+  // a run ending at the tile's last valid row may continue in the next tile
+  auto ends_at_tile_boundary = [&](int last_row, int dst) {
+    return last_row == n_valid - 1 && base + n_valid < n_rows && __ldg(a.e_dst + base + n_valid) == dst;
+  };
+  float pend[VEC];
+  int pend_dst = -1;
+  bool pend_start_boundary = false;
+#pragma unroll
+  for (int u = 0; u < VEC; ++u) pend[u] = 0.f;
+  float acc[VEC];
+#pragma unroll
+  for (int u = 0; u < VEC; ++u) acc[u] = 0.f;
+  int run_dst = -1, run_first_row = R0;
+  auto emit = [&](int last_row) {   // close the current run [run_first_row, last_row]
+    if (run_dst < 0) return;
+    const bool first_in_chunk = (run_first_row == R0);
+    if (first_in_chunk && R0 > 0 && prev_dst == run_dst) {   // continuation of a run owned by an earlier chunk: park it
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) s_P[warp * F + c0 + u] = acc[u];
+      return;
+    }
+    const bool start_boundary = first_in_chunk && R0 == 0 && prev_dst == run_dst;   // continues from the previous tile
+    const bool continues = (last_row == R0 + 7) && (R0 + 8 < TM) && row_dst(R0 + 8) == run_dst;
+    if (continues) {   // finished after the barrier, once the later chunks have parked their parts
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) pend[u] = acc[u];
+      pend_dst = run_dst;
+      pend_start_boundary = start_boundary;
+    } else {
+      write_out(run_dst, acc, start_boundary || ends_at_tile_boundary(last_row, run_dst));
+    }
+  };
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float xv[4][VEC], wv[4][VEC];
+    int dd[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int row = R0 + half * 4 + k;
+      dd[k] = row_dst(row);
+      if (dd[k] >= 0) {
+        const float* px = a.xcat + (size_t)s_src[row] * 192 + a.col0 + c0;
+        const float* pw = s_W + row * LDW + c0;
+        if (VEC == 4) {
+          const float4 x4 = __ldg(reinterpret_cast<const float4*>(px));
+          const float4 w4 = *reinterpret_cast<const float4*>(pw);
+          xv[k][0] = x4.x; xv[k][1] = x4.y; xv[k][VEC - 2] = x4.z; xv[k][VEC - 1] = x4.w;
+          wv[k][0] = w4.x; wv[k][1] = w4.y; wv[k][VEC - 2] = w4.z; wv[k][VEC - 1] = w4.w;
+        } else {
+          const float2 x2 = __ldg(reinterpret_cast<const float2*>(px));
+          const float2 w2 = *reinterpret_cast<const float2*>(pw);
+          xv[k][0] = x2.x; xv[k][1] = x2.y;
+          wv[k][0] = w2.x; wv[k][1] = w2.y;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) xv[k][u] = wv[k][u] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int row = R0 + half * 4 + k;
+      if (dd[k] != run_dst) {
+        emit(row - 1);
+        run_dst = dd[k];
+        run_first_row = row;
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) acc[u] = 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) acc[u] = fmaf(xv[k][u], wv[k][u], acc[u]);
+    }
+  }
+  emit(R0 + 7);
+  __syncthreads();   // parked continuation parts are visible
+  if (pend_dst >= 0) {
+    int last_row = R0 + 7;
+    for (int j = warp + 1; j < TCF_WARPS; ++j) {
+      if (row_dst(8 * j) != pend_dst) break;
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) pend[u] += s_P[j * F + c0 + u];
+      // last row of chunk j that still belongs to the run
+      int e = 8 * j;
+      while (e + 1 < 8 * j + 8 && row_dst(e + 1) == pend_dst) ++e;
+      last_row = e;
+      if (e != 8 * j + 7) break;
+    }
+    write_out(pend_dst, pend, pend_start_boundary || ends_at_tile_boundary(last_row, pend_dst));
+  }
+}
 
 template <int F>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltArgs a) {
@@ -47,6 +179,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
   constexpr uint32_t W2_HALF = (F / 32) * F * 128;     // K=F
   constexpr int PART_COLS = F / 4;                     // output columns owned by one of the 4 warp groups
   constexpr int CHUNKS = PART_COLS / 16;               // 2 (F=128) or 1 (F=64)
+  constexpr int LDW = TcFiltSmem<F>::LDW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer (LDS, not generic LD)
   uint8_t* wbuf = base;                                             // 128 KB, 1024-aligned
@@ -54,7 +187,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
   float* s_b1 = s_cw + 256;                                         // [F] layer-1 bias
   float* s_b2 = s_b1 + 128;                                         // [F] layer-2 bias
   float* s_dw = s_b2 + 128;                                         // [128] distance-weighting MLP
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dw + 128);         // [0]=weights landed, [1]=mma done
+  float* s_W = s_dw + 128;                                          // [128][LDW] filter tile awaiting aggregation
+  float* s_P = s_W + TM * LDW;                                      // [16][F] parked continuation sums
+  int* s_src = reinterpret_cast<int*>(s_P + TCF_WARPS * F);         // [2][128]
+  int* s_dst = s_src + 2 * TM;                                      // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dst + 2 * TM);     // [0]=weights landed, [1]=mma done
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -85,14 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
   uint32_t w_phase = 0, m_phase = 0;
   const float beta = __ldg(a.beta_ptr);
 
-  bool first_load = true;
   auto load_weights = [&](const float* img, uint32_t half_bytes) {   // tid 0 only: hi then lo, 16 KB pieces
-    if (a.debug_nostream && !first_load) {   // keep the barrier protocol, move 16 bytes instead of 128 KB
-      mbar_expect_tx(&bars[0], 16);
-      bulk_g2s(wbuf, img, 16, &bars[0]);
-      return;
-    }
-    first_load = false;
     mbar_expect_tx(&bars[0], 2 * half_bytes);
     const uint8_t* src = reinterpret_cast<const uint8_t*>(img);
     for (uint32_t off = 0; off < 2 * half_bytes; off += 16384) bulk_g2s(wbuf + off, src + off, 16384, &bars[0]);
@@ -128,13 +258,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
   prefetch(blockIdx.x);
 
   int it = 0;
+  int64_t prev_base = 0;
+  int prev_valid = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     float* cwbuf = s_cw + (it & 1) * 128;
     const int64_t row0 = static_cast<int64_t>(tile) * TM;
     const int64_t r = row0 + my_row;
     const bool valid = r < n_rows;
-    // ---- stage A = g2 tile (hi/lo) into TMEM from the prefetched registers; envelope weight into smem
+    // ---- stage A = g2 tile (hi/lo) into TMEM from the prefetched registers; envelope weight / edge endpoints into smem
     if (part == 3) cwbuf[my_row] = valid ? cfconv_edge_weight_smem(pre_len, s_dw, a.cutoff, a.smooth) : 0.f;
+    if (part == 2 && a.fuse) {
+      s_src[(it & 1) * TM + my_row] = valid ? __ldg(a.e_src + r) : 0;
+      s_dst[(it & 1) * TM + my_row] = valid ? __ldg(a.e_dst + r) : -1;
+    }
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t hi[16], lo[16];
@@ -143,9 +279,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
         const float4 v = pre[c * 4 + q];
         const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          split_tf32(vv[j], hi[q * 4 + j], lo[q * 4 + j]);
-        }
+        for (int j = 0; j < 4; ++j) split_tf32(vv[j], hi[q * 4 + j], lo[q * 4 + j]);
       }
       tmem_st16(trow + COL_AHI + part * 32 + c * 16, hi);
       tmem_st16(trow + COL_ALO + part * 32 + c * 16, lo);
@@ -161,6 +295,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
     }
     w_phase ^= 1;
     prefetch(tile + static_cast<int>(gridDim.x));    // next tile's operand rows travel while the tensor core works
+    // ---- ... and the previous tile's filters are reduced into agg (s_W was completed before the barrier above)
+    if (a.fuse && it > 0)
+      aggregate_tile<F>(a, s_W, s_src + ((it - 1) & 1) * TM, s_dst + ((it - 1) & 1) * TM, s_P, prev_base, prev_valid, n_rows, warp, lane);
     mbar_wait(&bars[1], m_phase);
     m_phase ^= 1;
     fence_after_sync();
@@ -197,13 +334,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
     m_phase ^= 1;
     fence_after_sync();
     if (tid == 0 && tile + static_cast<int>(gridDim.x) < n_tiles) load_weights(a.W1img, W1_HALF);
-    // ---- epilogue 2: W = (D + b2) * cw -> global filt[e][col0 + n]
+    // ---- epilogue 2: W = (D + b2) * cw -> shared filter tile (fused) or global filt[e][col0 + n]
     const float cw = cwbuf[my_row];
     {
       float v[16 * CHUNKS];
       const int nb = part * PART_COLS;
       if constexpr (CHUNKS == 2) tmem_ld32_main(trow, nb, v); else tmem_ld16_main(trow, nb, v);
-      if (valid) {
+      if (a.fuse) {
+        float4* dst = reinterpret_cast<float4*>(s_W + my_row * LDW + nb);
+#pragma unroll
+        for (int q = 0; q < 4 * CHUNKS; ++q)
+          dst[q] = make_float4((v[q * 4 + 0] + s_b2[nb + q * 4 + 0]) * cw, (v[q * 4 + 1] + s_b2[nb + q * 4 + 1]) * cw,
+                               (v[q * 4 + 2] + s_b2[nb + q * 4 + 2]) * cw, (v[q * 4 + 3] + s_b2[nb + q * 4 + 3]) * cw);
+      } else if (valid) {
         float4* dst = reinterpret_cast<float4*>(a.filt + r * 192 + a.col0 + nb);
 #pragma unroll
         for (int q = 0; q < 4 * CHUNKS; ++q) {
@@ -216,15 +359,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_filter_kernel(const TcFiltAr
         }
       }
     }
+    prev_base = row0;
+    prev_valid = (n_rows - row0 < TM) ? static_cast<int>(n_rows - row0) : TM;
     // no barrier here: the next tile's operand stores target the A columns (dead since layer 2 completed), its envelope
-    // weights go to the other s_cw buffer, and D is only overwritten after the next tile's post-staging barrier
+    // weights / endpoints go to the other smem buffers, D is only overwritten after the next tile's post-staging barrier
+    // (which also publishes s_W to the aggregation of this tile)
   }
+  __syncthreads();
+  if (a.fuse && it > 0)
+    aggregate_tile<F>(a, s_W, s_src + ((it - 1) & 1) * TM, s_dst + ((it - 1) & 1) * TM, s_P, prev_base, prev_valid, n_rows, warp, lane);
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// Measured on B200 (22.6 k atoms, 761 k edges): fused 5.04 ms per network evaluation vs 4.86 ms for filter kernels + the
+// separate HBM-streaming aggregate kernel -- the reduction is only partly hidden under the layer-1 MMA window -- and the
+// fused sum order depends on how a destination's edges fall into 8-row chunks, i.e. on batch composition (the separate
+// kernel sums each destination sequentially).  Hence opt-in: AGD_TC_FUSE_AGG=1.
+static int tc_fuse_default() {
+  const char* e = std::getenv("AGD_TC_FUSE_AGG");
+  return (e && e[0] == '1') ? 1 : 0;
+}
+
 void launch_filters_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& mw, int blk) {
   const BlkW& w = mw.blk[blk];
+  static const int fuse = tc_fuse_default();
   TcFiltArgs a{};
   a.n_rows_dev = b.counters;
   a.g2 = b.g2;
@@ -232,20 +391,27 @@ void launch_filters_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& mw, 
   a.filt = b.filt;
   a.cutoff = c.cutoff;
   a.smooth = c.smooth;
-  { const char* e = getenv("AGD_TC_NOSTREAM"); a.debug_nostream = (e && e[0] == '1') ? 1 : 0; }
+  a.fuse = fuse;
+  a.xcat = b.xcat;
+  a.agg = b.agg;
+  a.e_src = b.e_src;
+  a.e_dst = b.e_dst;
+  if (fuse) cudaMemsetAsync(b.agg, 0, sizeof(float) * 192 * (size_t)b.n_atoms, c.stream);
   int64_t tiles = (b.cap + TM - 1) / TM;
   const int grid = (int)(tiles < c.num_sms ? (tiles < 1 ? 1 : tiles) : c.num_sms);
   a.W1img = w.tF1a; a.W2img = w.tF2a; a.f1b = w.f1ab; a.f2b = w.f2ab; a.dw = w.dw1; a.beta_ptr = w.sc + 0; a.col0 = 0;
-  tc_filter_kernel<128><<<grid, TC_THREADS, TC_FILT_SMEM, c.stream>>>(a);
-  note_launch(c, "schnet.filter128_tc");
+  tc_filter_kernel<128><<<grid, TC_THREADS, TcFiltSmem<128>::bytes, c.stream>>>(a);
+  note_launch(c, fuse ? "schnet.cfconv128_tc" : "schnet.filter128_tc");
   a.W1img = w.tF1b; a.W2img = w.tF2b; a.f1b = w.f1bb; a.f2b = w.f2bb; a.dw = w.dw2; a.beta_ptr = w.sc + 1; a.col0 = 128;
-  tc_filter_kernel<64><<<grid, TC_THREADS, TC_FILT_SMEM, c.stream>>>(a);
-  note_launch(c, "schnet.filter64_tc");
+  tc_filter_kernel<64><<<grid, TC_THREADS, TcFiltSmem<64>::bytes, c.stream>>>(a);
+  note_launch(c, fuse ? "schnet.cfconv64_tc" : "schnet.filter64_tc");
 }
 
+bool filters_tc_fused() { return tc_fuse_default() != 0; }
+
 void set_tc_attributes() {
-  cudaFuncSetAttribute(tc_filter_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_FILT_SMEM);
-  cudaFuncSetAttribute(tc_filter_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_FILT_SMEM);
+  cudaFuncSetAttribute(tc_filter_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcFiltSmem<128>::bytes);
+  cudaFuncSetAttribute(tc_filter_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcFiltSmem<64>::bytes);
 }
 
 }  // namespace agd

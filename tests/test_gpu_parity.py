@@ -257,7 +257,7 @@ def test_sampler_properties():
     z, bi, bt, b, G, pos = _batch("qm9", seed=6, scale=1.0)
     args = (z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), G)
     kw = dict(extend_order=False, n_steps=20, step_lr=1e-6, clip=1000.0, clip_local=20.0, global_start_sigma=0.5,
-              w_global=1.0, return_traj=False)
+              w_global=1.0, return_traj=False, t_start=2022, scale_init=False)      # 10 local-only + 10 global steps
     p1, t1 = m.langevin_dynamics_sample(*args, seed=11, **kw)       # dispatcher, reference dualenc.py:397
     p2, _ = m.langevin_dynamics_sample_diffusion(*args, seed=11, **kw)
     p3, _ = m.langevin_dynamics_sample_diffusion(*args, seed=12, **kw)
