@@ -21,7 +21,7 @@ EXPORTS = [
     "agd_weight_slot_name", "agd_weight_slot_size", "agd_load_weights", "agd_batch_workspace_bytes",
     "agd_batch_create", "agd_batch_destroy", "agd_build_edges", "agd_forward", "agd_sample",
     "agd_extend_bond_order", "agd_op_cfconv_aggregate", "agd_op_eq_transform", "agd_debug_fetch",
-    "agd_launch_count", "agd_profile_forward",
+    "agd_launch_count", "agd_profile_forward", "agd_forward_edges",
 ]
 
 
@@ -53,6 +53,14 @@ class SampleParams(C.Structure):
                 ("w_global", C.c_float), ("clip", C.c_float), ("clip_local", C.c_float), ("clip_pos", C.c_float),
                 ("seed", C.c_uint64), ("noise", C.c_void_p), ("traj", C.c_void_p), ("use_cuda_graph", C.c_int32),
                 ("step_offset", C.c_int32)]
+
+
+class EdgeSet(C.Structure):
+    _fields_ = [("n_edges", C.c_int32),
+                ("e_src", C.c_void_p), ("e_dst", C.c_void_p), ("e_type", C.c_void_p), ("e_canon", C.c_void_p),
+                ("e_len", C.c_void_p), ("in_ptr", C.c_void_p), ("out_ptr", C.c_void_p),
+                ("c_src", C.c_void_p), ("c_dst", C.c_void_p), ("c_type", C.c_void_p), ("c_len", C.c_void_p),
+                ("lc_len", C.c_void_p)]
 
 
 class ForwardOut(C.Structure):
@@ -91,6 +99,7 @@ def load() -> C.CDLL:
     lib.agd_batch_destroy.restype = None
     lib.agd_build_edges.argtypes = [vp, vp, vp, C.POINTER(ForwardOut), vp]
     lib.agd_forward.argtypes = [vp, vp, vp, C.POINTER(ForwardOut), vp]
+    lib.agd_forward_edges.argtypes = [vp, vp, vp, C.POINTER(EdgeSet), C.POINTER(ForwardOut), vp]
     lib.agd_sample.argtypes = [vp, vp, vp, C.POINTER(SampleParams), C.POINTER(i32), vp]
     lib.agd_extend_bond_order.argtypes = [vp, i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.agd_op_cfconv_aggregate.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]

@@ -163,8 +163,8 @@ static void run_local_branch(const LaunchCtx& c, const BatchDev& b, const ModelW
   if (h_out) *h_out = x_in;
 }
 
-static void run_global_branch(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos) {
-  launch_build_edges(c, b, pos);
+static void run_global_branch(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos, bool build = true) {
+  if (build) launch_build_edges(c, b, pos);
   if (c.use_tc) launch_encoder_global_tc(c, b, w); else launch_encoder_global(c, b, w);
   if (c.use_tc) launch_schnet_node_tc(c, b, w, -1); else launch_schnet_node(c, b, w, -1);
   for (int k = 0; k < c.num_convs; ++k) {
@@ -400,6 +400,32 @@ int agd_forward(agd_handle* h, agd_batch* b, const float* pos, const agd_forward
   run_global_branch(c, b->d, h->w, pos);
   run_local_branch(c, b->d, h->w, pos, nullptr);
   launch_export_edges(c, b->d, *out, true);
+  return leave(h, stream);
+}
+
+int agd_forward_edges(agd_handle* h, agd_batch* b, const float* pos, const agd_edge_set* es, const agd_forward_out* out, void* stream) {
+  int rc = check_ready(h, b);
+  if (rc) return rc;
+  if (!pos || !es || !out) return fail(AGD_ERR_INVALID, "null argument");
+  if (es->n_edges < 0 || es->n_edges > b->d.cap) return fail(AGD_ERR_CAPACITY, "edge set exceeds the batch capacity");
+  if ((rc = enter(h, stream))) return rc;
+  BatchDev& d = b->d;
+  const size_t E = (size_t)es->n_edges, N = (size_t)d.n_atoms;
+  auto cp = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, h->stream); };
+  CUDA_TRY(cp(d.e_src, es->e_src, E * 4)); CUDA_TRY(cp(d.e_dst, es->e_dst, E * 4)); CUDA_TRY(cp(d.e_type, es->e_type, E * 4));
+  CUDA_TRY(cp(d.e_canon, es->e_canon, E * 4)); CUDA_TRY(cp(d.e_len, es->e_len, E * 4));
+  CUDA_TRY(cp(d.in_ptr, es->in_ptr, (N + 1) * 4)); CUDA_TRY(cp(d.out_ptr, es->out_ptr, (N + 1) * 4));
+  CUDA_TRY(cp(d.c_src, es->c_src, E * 4)); CUDA_TRY(cp(d.c_dst, es->c_dst, E * 4)); CUDA_TRY(cp(d.c_type, es->c_type, E * 4));
+  CUDA_TRY(cp(d.c_len, es->c_len, E * 4));
+  const int n = es->n_edges;
+  CUDA_TRY(cudaMemcpyAsync(d.counters, &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));   // `n` lives on this stack frame
+  LaunchCtx c = make_ctx(h);
+  run_global_branch(c, d, h->w, pos, /*build=*/false);
+  d.lc_len_in = es->lc_len;
+  run_local_branch(c, d, h->w, pos, nullptr);
+  d.lc_len_in = nullptr;
+  launch_export_edges(c, d, *out, true);
   return leave(h, stream);
 }
 

@@ -28,6 +28,7 @@ struct EncArgs {
   const float* pos;
   const int *src, *dst, *canon;
   float *len_csc, *len_canon;
+  const float* len_in;     // local: caller-supplied lengths instead of |pos[src]-pos[dst]|
   float* out;              // g2 (global) or edge_attr (local), [rows][128]
 };
 
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(NT, 2) edge_encoder_kernel(const EncArgs a) {
           const float dx = a.pos[3 * (size_t)s] - a.pos[3 * (size_t)q];
           const float dy = a.pos[3 * (size_t)s + 1] - a.pos[3 * (size_t)q + 1];
           const float dz = a.pos[3 * (size_t)s + 2] - a.pos[3 * (size_t)q + 2];
-          d = sqrtf(dx * dx + dy * dy + dz * dz);
+          d = a.len_in ? a.len_in[r] : sqrtf(dx * dx + dy * dy + dz * dz);
           a.len_csc[r] = d;
           a.len_canon[a.canon[r]] = d;
         } else {
@@ -201,6 +202,7 @@ void launch_encoder_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w
   a.canon = b.lc_canon;
   a.len_csc = b.lc_len;
   a.len_canon = b.lcc_len;
+  a.len_in = b.lc_len_in;
   a.out = b.ea_loc;
   edge_encoder_kernel<true><<<tiles_grid(b.n_local, c.num_sms, 2), NT, ENC_SMEM, c.stream>>>(a);
   note_launch(c, "encoder.local");

@@ -79,6 +79,7 @@ struct BatchDev {
   float *s_csc, *s_canon;        // edge_inv_global
   // local edges
   float *lc_len, *lcc_len;       // CSC / canonical
+  const float* lc_len_in;        // caller-supplied local edge lengths (CSC order) or nullptr: computed from pos
   float *sl_csc, *sl_canon;      // edge_inv_local
   float* ea_loc;                 // [n_local][128]
   // activations

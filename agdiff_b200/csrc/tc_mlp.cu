@@ -83,6 +83,7 @@ struct TcEncArgs {
   const float* pos;               // local: lengths from positions
   const int *src, *dst, *canon;
   float *len_csc, *len_canon;
+  const float* len_in;            // local: caller-supplied lengths instead of |pos[src]-pos[dst]|
   float* out;                     // g2 (global) / edge_attr (local) [rows][128]
 };
 
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) tc_encoder_kernel(const TcEncA
         const float dx = a.pos[3 * (size_t)s] - a.pos[3 * (size_t)q];
         const float dy = a.pos[3 * (size_t)s + 1] - a.pos[3 * (size_t)q + 1];
         const float dz = a.pos[3 * (size_t)s + 2] - a.pos[3 * (size_t)q + 2];
-        d = sqrtf(dx * dx + dy * dy + dz * dz);
+        d = a.len_in ? __ldg(a.len_in + r) : sqrtf(dx * dx + dy * dy + dz * dz);
         if (part == 0) {
           a.len_csc[r] = d;
           a.len_canon[__ldg(a.canon + r)] = d;
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) tc_encoder_kernel(const TcEncA
       float t[16];
       const int k0 = part * 32 + c * 16;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) t[j] = gelu_erf(fmaf(s_few[k0 + j], d, s_feb[k0 + j]));
+      for (int j = 0; j < 16; ++j) t[j] = gelu_fast(fmaf(s_few[k0 + j], d, s_feb[k0 + j]));
       store_split16(cx.trow + COL_AHI + k0, cx.trow + COL_ALO + k0, t);
     }
     cx.layer_streamed(128, 128, false);                 // edge_feature_mlp.0 (x half)
@@ -173,10 +174,10 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) tc_encoder_kernel(const TcEncA
       tmem_ld16_acc(cx.trow, n0, v);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        t[q * 4 + 0] = gelu_erf(v[q * 4 + 0] + tb[q].x);
-        t[q * 4 + 1] = gelu_erf(v[q * 4 + 1] + tb[q].y);
-        t[q * 4 + 2] = gelu_erf(v[q * 4 + 2] + tb[q].z);
-        t[q * 4 + 3] = gelu_erf(v[q * 4 + 3] + tb[q].w);
+        t[q * 4 + 0] = gelu_fast(v[q * 4 + 0] + tb[q].x);
+        t[q * 4 + 1] = gelu_fast(v[q * 4 + 1] + tb[q].y);
+        t[q * 4 + 2] = gelu_fast(v[q * 4 + 2] + tb[q].z);
+        t[q * 4 + 3] = gelu_fast(v[q * 4 + 3] + tb[q].w);
       }
       store_split16(cx.trow + COL_AHI + n0, cx.trow + COL_ALO + n0, t);
     }
@@ -199,10 +200,10 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) tc_encoder_kernel(const TcEncA
       tmem_ld16_acc(cx.trow, n0, v);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        t[q * 4 + 0] = gelu_erf(v[q * 4 + 0] + tb[q].x);
-        t[q * 4 + 1] = gelu_erf(v[q * 4 + 1] + tb[q].y);
-        t[q * 4 + 2] = gelu_erf(v[q * 4 + 2] + tb[q].z);
-        t[q * 4 + 3] = gelu_erf(v[q * 4 + 3] + tb[q].w);
+        t[q * 4 + 0] = gelu_fast(v[q * 4 + 0] + tb[q].x);
+        t[q * 4 + 1] = gelu_fast(v[q * 4 + 1] + tb[q].y);
+        t[q * 4 + 2] = gelu_fast(v[q * 4 + 2] + tb[q].z);
+        t[q * 4 + 3] = gelu_fast(v[q * 4 + 3] + tb[q].w);
       }
       if (LOCAL) {
         store_split16(cx.trow + COL_AHI + n0, cx.trow + COL_ALO + n0, t);
@@ -417,7 +418,7 @@ void launch_encoder_local_tc(const LaunchCtx& c, const BatchDev& b, const ModelW
   a.w = w.enc; a.tW1 = w.tenc_W1; a.tM2 = w.tenc_M2; a.tC2 = w.tenc_C2;
   a.n_rows_dev = nullptr; a.n_rows_static = b.n_local;
   a.e_type = b.lc_type; a.pos = pos; a.src = b.lc_src; a.dst = b.lc_dst; a.canon = b.lc_canon;
-  a.len_csc = b.lc_len; a.len_canon = b.lcc_len; a.out = b.ea_loc;
+  a.len_csc = b.lc_len; a.len_canon = b.lcc_len; a.len_in = b.lc_len_in; a.out = b.ea_loc;
   tc_encoder_kernel<true><<<tc_grid(b.n_local, c.num_sms), TCM_THREADS, TC_ENC_SMEM, c.stream>>>(a);
   note_launch(c, "encoder.local_tc");
 }

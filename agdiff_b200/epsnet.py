@@ -175,7 +175,7 @@ def _csr_ptr(idx: torch.Tensor, n: int) -> torch.Tensor:
 class NativeBatch:
     """Device topology of one (sub-)batch plus the library workspace handle."""
 
-    def __init__(self, model: "DualEncoderEpsNetwork", atom_type, st_row, st_col, st_type, batch, mol_gid=None):
+    def __init__(self, model: "DualEncoderEpsNetwork", atom_type, st_row, st_col, st_type, batch, mol_gid=None, min_cap=0):
         lib = _lib.load()
         dev = atom_type.device
         N = int(atom_type.numel())
@@ -221,7 +221,7 @@ class NativeBatch:
         # capacity: in-degree <= min(n_mol, 33 + static in-degree)
         n_of_atom = counts[batch]
         cap = torch.minimum(n_of_atom, (st_in[1:] - st_in[:-1]) + (_lib.MAX_RADIUS_NBRS + 1)).sum()
-        self.cap = int(cap.item())
+        self.cap = max(int(cap.item()), int(min_cap))
         self.atom_type = _i32(atom_type)
         self.mol_ptr = _i32(mol_ptr)
         self.atom_mol = _i32(batch)
@@ -415,15 +415,15 @@ class DualEncoderEpsNetwork(nn.Module):
     def forward(self, atom_type, pos, bond_index, bond_type, batch, time_step, edge_index=None, edge_type=None,
                 edge_length=None, return_edges=False, extend_order=True, extend_radius=True):
         """reference dualenc.py:142-251; ``time_step`` is unused there as well."""
-        if edge_index is not None and edge_type is not None and edge_length is not None:
-            raise NotImplementedError("caller-supplied edge lists are not on the native path yet; pass None to have "
-                                      "them rebuilt (what every reference caller does)")
-        if not extend_radius:
-            raise NotImplementedError("extend_radius=False is not on the native path (no reference caller uses it)")
         dev = self._device()
         atom_type = atom_type.to(dev)
         self._renorm_embedding(atom_type)
         self._sync_weights()
+        given = edge_index is not None and edge_type is not None and edge_length is not None
+        if given or not extend_radius:
+            res = self._forward_preset(atom_type, pos, bond_index, bond_type, batch, edge_index, edge_type, edge_length,
+                                       extend_order, given)
+            return res if return_edges else res[:2]
         nb = self._prepare(atom_type, bond_index, bond_type, batch, extend_order)
         try:
             res = self._forward_native(nb, pos)
@@ -454,6 +454,52 @@ class DualEncoderEpsNetwork(nn.Module):
         if build_only:
             return edge_index, edge_type, edge_length
         return (eg[:E].unsqueeze(-1), el[:nb.n_local].unsqueeze(-1), edge_index, edge_type, edge_length, edge_type > 0)
+
+    def _forward_preset(self, atom_type, pos, bond_index, bond_type, batch, edge_index, edge_type, edge_length, extend_order,
+                        given):
+        """forward on an edge list that is NOT rebuilt from positions: caller-supplied edges (reference dualenc.py:166 only
+        rebuilds when one of the three is None) or extend_radius=False (the bond / order-extended graph, common.py:236-264).
+        The caller's edge order is kept for every output, like the reference does."""
+        lib, dev = _lib.load(), self._device()
+        pos = pos.to(dev, torch.float32).contiguous()
+        batch = batch.to(dev)
+        N = atom_type.numel()
+        if given:
+            row, col = edge_index[0].to(dev).long(), edge_index[1].to(dev).long()
+            typ = edge_type.to(dev).long()
+            length = edge_length.to(dev, torch.float32).reshape(-1).contiguous()
+        else:
+            bond_index, bond_type = bond_index.to(dev), bond_type.to(dev)
+            if extend_order:
+                row, col, typ = self._static_edges(N, bond_index, bond_type, batch, True)
+            else:                                   # the reference returns the bond list untouched (not coalesced)
+                row, col, typ = bond_index[0].long(), bond_index[1].long(), bond_type.long()
+            length = (pos[row] - pos[col]).norm(dim=-1)          # get_distance, geometry.py:5-6
+        E = int(row.numel())
+        if E and (int(typ.max().item()) >= 100 or int(typ.min().item()) < 0):
+            raise IndexError("edge_type out of range for Embedding(100, ...)")
+        lmask = typ > 0
+        nb = NativeBatch(self, atom_type, row[lmask], col[lmask], typ[lmask], batch, None, min_cap=E)
+        try:
+            perm = torch.argsort(col * N + row, stable=True)
+            es = _lib.EdgeSet()
+            keep = [_i32(row[perm]), _i32(col[perm]), _i32(typ[perm]), _i32(perm), length[perm].contiguous(),
+                    _i32(_csr_ptr(col, N)), _i32(_csr_ptr(row, N)), _i32(row), _i32(col), _i32(typ), length,
+                    length[lmask][nb.lc_canon.long()].contiguous() if nb.n_local else length.new_zeros(1)]
+            es.n_edges = E
+            (es.e_src, es.e_dst, es.e_type, es.e_canon, es.e_len, es.in_ptr, es.out_ptr, es.c_src, es.c_dst, es.c_type, es.c_len,
+             es.lc_len) = [_ptr(t) for t in keep]
+            cap = max(nb.cap, 1)
+            eg = torch.empty(cap, dtype=torch.float32, device=dev)
+            el = torch.empty(max(nb.n_local, 1), dtype=torch.float32, device=dev)
+            out = _lib.ForwardOut(_ptr(eg), _ptr(el), None, None, None, None, None)
+            torch.cuda.synchronize(dev)
+            _lib.check(lib.agd_forward_edges(self._native_handle(), nb.handle, _ptr(pos), C.byref(es), C.byref(out), self._stream()))
+            torch.cuda.current_stream(dev).synchronize()
+        finally:
+            nb.close()
+        ei = torch.stack([row, col])
+        return (eg[:E].unsqueeze(-1), el[:nb.n_local].unsqueeze(-1), ei, typ, length.unsqueeze(-1), lmask)
 
     def build_edges(self, pos, bond_index, bond_type, batch, extend_order=True):
         """extend_graph_order_radius + get_distance (reference common.py:236-264, geometry.py:5-6)."""

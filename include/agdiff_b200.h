@@ -136,6 +136,23 @@ int agd_build_edges(agd_handle* h, agd_batch* b, const float* pos_dev, const agd
  * for a batch whose static edges are already order-extended. */
 int agd_forward(agd_handle* h, agd_batch* b, const float* pos_dev, const agd_forward_out* out, void* stream);
 
+/* forward with caller-supplied edges (dualenc.py:166: edges are only rebuilt when one of edge_index / edge_type /
+ * edge_length is None) and for extend_radius=False.  All arrays are device pointers; the edge list is given in CSC order
+ * (grouped by edge_index[1], sources ascending) with its canonical bookkeeping, exactly what agd_build_edges produces
+ * internally; the host mirror derives it from the caller's canonical list.  The batch's local lists (lc_*) must be the
+ * type > 0 subset of this edge list. */
+typedef struct {
+  int32_t n_edges;
+  const int32_t *e_src, *e_dst, *e_type, *e_canon;   /* dev [n_edges], CSC order; e_canon = position in the caller's order */
+  const float* e_len;                                 /* dev [n_edges] */
+  const int32_t *in_ptr, *out_ptr;                    /* dev [n_atoms+1] */
+  const int32_t *c_src, *c_dst, *c_type;              /* dev [n_edges], caller's (canonical) order */
+  const float* c_len;
+  const float* lc_len;                                /* dev [n_local] lengths of the local edges, CSC order */
+} agd_edge_set;
+int agd_forward_edges(agd_handle* h, agd_batch* b, const float* pos_dev, const agd_edge_set* edges, const agd_forward_out* out,
+                      void* stream);
+
 /* langevin_dynamics_sample_diffusion loop body x n_steps (dualenc.py:476-545), in place on pos.
  * first_nan_step (host, may be NULL) receives the first step whose update produced NaN or -1;
  * the call returns AGD_ERR_NAN in that case (the host mirror raises FloatingPointError). */

@@ -190,6 +190,41 @@ def test_forward_extend_order_default():
     assert torch.equal(eg2, out[0]) and torch.equal(el2, out[1])
 
 
+def test_forward_with_supplied_edges_and_without_radius():
+    """dualenc.py:166: edges are only rebuilt when one of edge_index/edge_type/edge_length is None; extend_radius=False
+    keeps the (order-extended) bond graph.  Supplied lengths are used as given, the caller's edge order is kept."""
+    m, sd = _cuda_model("drugs", 2021, 4)
+    cfg = CONFIGS["drugs"]
+    mols = synth.qm9_like(6, seed=13) + synth.drugs_like(3, seed=14, force_max=False)
+    z, bi, bt, b, G = graph.collate(mols, 1)
+    gen = torch.Generator().manual_seed(9)
+    pos0 = torch.randn(z.numel(), 3, generator=gen) * 2.0
+    pos1 = pos0 + 0.3 * torch.randn(z.numel(), 3, generator=gen)          # forward at other positions than the edges' lengths
+    ei, et = O.build_edges(pos0, bi, bt, b, cfg, extend_order=True)
+    elen = O.edge_lengths(pos0, ei).unsqueeze(-1)
+    shuf = torch.randperm(ei.size(1), generator=gen)                      # the caller's order is arbitrary
+    ei, et, elen = ei[:, shuf], et[shuf], elen[shuf]
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, z, pos1, bi, bt, b, edges=(ei, et, elen))
+    out = m(z.to(DEV), pos1.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), None, edge_index=ei.to(DEV), edge_type=et.to(DEV),
+            edge_length=elen.to(DEV), return_edges=True)
+    assert torch.equal(out[2].cpu(), ei) and torch.equal(out[3].cpu(), et) and torch.equal(out[4].cpu(), elen)
+    assert torch.equal(out[5].cpu(), et > 0)
+    assert_close(out[0], ref[0], what="edge_inv_global (supplied edges)", extra_atol=1e-5)
+    assert_close(out[1], ref[1], what="edge_inv_local (supplied edges)", extra_atol=1e-4)
+    for extend_order in (True, False):
+        bi_in, bt_in = (bi, bt) if extend_order else (bi.flip(1), bt.flip(0))      # unsorted list is returned untouched
+        with torch.no_grad():
+            ref = O.forward(sd, cfg, z, pos1, bi_in, bt_in, b, extend_order=extend_order, extend_radius=False)
+        out = m(z.to(DEV), pos1.to(DEV), bi_in.to(DEV), bt_in.to(DEV), b.to(DEV), None, return_edges=True,
+                extend_order=extend_order, extend_radius=False)
+        assert torch.equal(out[2].cpu(), ref[2]) and torch.equal(out[3].cpu(), ref[3])
+        assert bool(out[5].all()) and out[0].shape == ref[0].shape
+        assert_close(out[4], ref[4], rtol=1e-6, atol_scale=1e-7, what="edge_length (no radius)")
+        assert_close(out[0], ref[0], what="edge_inv_global (no radius)", extra_atol=1e-5)
+        assert_close(out[1], ref[1], what="edge_inv_local (no radius)", extra_atol=1e-4)
+
+
 def test_state_dict_roundtrip_and_renorm_side_effect():
     m, sd = _cuda_model("qm9", 2021, 8)
     m2, _ = _cuda_model("qm9", 1, 0)
