@@ -15,6 +15,8 @@ Extensions (keyword-only, all optional, defaults reproduce the reference behavio
   return_traj=bool             False skips the per-step trajectory (reference always keeps it)
   mol_gid=(G,) int64           global molecule ids keying the noise streams (multi-GPU sharding)
   use_cuda_graph=bool          replay captured per-step graphs (default True)
+  max_chunk_edges=int          very large batches are sampled in independent molecule chunks of at most this many
+                               (capacity-bound) edges each, default 8e6; exact, molecules do not interact
 """
 from __future__ import annotations
 
@@ -572,43 +574,67 @@ class DualEncoderEpsNetwork(nn.Module):
             if noise is not None:
                 noise = noise.to(dev, torch.float32).contiguous()
                 assert noise.shape == (n_steps, N, 3)
-            nb = self._prepare(atom_type, bond_index, bond_type, batch, extend_order, kwargs.get("mol_gid"))
-            traj_host = None
-            try:
-                if return_traj and n_steps > 0:
-                    traj_host = torch.empty((n_steps, N, 3), dtype=torch.float32, pin_memory=True)
-                    tbuf = torch.empty((min(window, n_steps), N, 3), dtype=torch.float32, device=dev)
-                    spans = [(s, min(s + window, n_steps)) for s in range(0, n_steps, window)]
-                else:
-                    tbuf = None
-                    spans = [(0, n_steps)] if n_steps > 0 else []
-                for s0, s1 in spans:
-                    p = _lib.SampleParams()
-                    p.n_steps = s1 - s0
-                    p.sigma = sig[s0:s1].ctypes.data_as(C.c_void_p)
-                    p.step_size = stp[s0:s1].ctypes.data_as(C.c_void_p)
-                    p.noise_scale = nsc[s0:s1].ctypes.data_as(C.c_void_p)
-                    p.use_global = glb[s0:s1].ctypes.data_as(C.c_void_p)
-                    p.w_global, p.clip = float(w_global), float(clip)
-                    p.clip_local = -1.0 if clip_local is None else float(clip_local)
-                    p.clip_pos = -1.0 if clip_pos is None else float(clip_pos)
-                    p.seed = seed
-                    p.step_offset = s0
-                    p.noise = _ptr(noise[s0:s1]) if noise is not None else None
-                    p.traj = _ptr(tbuf) if tbuf is not None else None
-                    p.use_cuda_graph = 1 if use_graph else 0
-                    nan_step = C.c_int32(-1)
-                    rc = lib.agd_sample(self._native_handle(), nb.handle, _ptr(pos), C.byref(p), C.byref(nan_step),
-                                        self._stream())
-                    if rc == _lib.AGD_ERR_NAN:
-                        print("NaN detected. Please restart.")
-                        raise FloatingPointError()
-                    _lib.check(rc)
-                    if tbuf is not None:
-                        traj_host[s0:s1].copy_(tbuf[: s1 - s0], non_blocking=True)
-                        torch.cuda.current_stream(dev).synchronize()
-            finally:
-                nb.close()
+            # canonical static edges once, then independent molecule chunks (exact: results do not depend on batch composition)
+            batch = batch.to(dev)
+            row, col, typ = self._static_edges(N, bond_index.to(dev), bond_type.to(dev), batch, extend_order)
+            G = int(batch[-1].item()) + 1
+            counts = torch.bincount(batch, minlength=G)
+            st_in = torch.bincount(col, minlength=N)
+            cap_mol = torch.zeros(G, dtype=torch.long, device=dev).index_add_(
+                0, batch, torch.minimum(counts[batch], st_in + (_lib.MAX_RADIUS_NBRS + 1)))
+            max_edges = int(kwargs.get("max_chunk_edges", 8_000_000))
+            bounds, start, acc = [], 0, 0
+            for g, c in enumerate(cap_mol.cpu().tolist()):
+                if acc + c > max_edges and g > start:
+                    bounds.append((start, g))
+                    start, acc = g, 0
+                acc += c
+            bounds.append((start, G))
+            mol_ptr = torch.zeros(G + 1, dtype=torch.long, device=dev)
+            mol_ptr[1:] = torch.cumsum(counts, 0)
+            mol_ptr_h = mol_ptr.cpu().tolist()
+            gid_all = kwargs.get("mol_gid")
+            gid_all = torch.arange(G, dtype=torch.long, device=dev) if gid_all is None else gid_all.to(dev)
+            traj_host = torch.empty((n_steps, N, 3), dtype=torch.float32, pin_memory=True) if (return_traj and n_steps > 0) else None
+            spans = ([(s, min(s + window, n_steps)) for s in range(0, n_steps, window)] if traj_host is not None
+                     else ([(0, n_steps)] if n_steps > 0 else []))
+            for g0, g1 in bounds:
+                a0, a1 = mol_ptr_h[g0], mol_ptr_h[g1]
+                e0, e1 = (int(v) for v in torch.searchsorted(row, torch.tensor([a0, a1], device=dev)).tolist())
+                nb = NativeBatch(self, atom_type[a0:a1], row[e0:e1] - a0, col[e0:e1] - a0, typ[e0:e1], batch[a0:a1] - g0,
+                                 gid_all[g0:g1])
+                pos_c = pos[a0:a1]                       # contiguous row slice of `pos`: updated in place
+                noise_c = noise[:, a0:a1].contiguous() if noise is not None else None
+                tbuf = (torch.empty((min(window, n_steps), a1 - a0, 3), dtype=torch.float32, device=dev)
+                        if traj_host is not None else None)
+                try:
+                    for s0, s1 in spans:
+                        p = _lib.SampleParams()
+                        p.n_steps = s1 - s0
+                        p.sigma = sig[s0:s1].ctypes.data_as(C.c_void_p)
+                        p.step_size = stp[s0:s1].ctypes.data_as(C.c_void_p)
+                        p.noise_scale = nsc[s0:s1].ctypes.data_as(C.c_void_p)
+                        p.use_global = glb[s0:s1].ctypes.data_as(C.c_void_p)
+                        p.w_global, p.clip = float(w_global), float(clip)
+                        p.clip_local = -1.0 if clip_local is None else float(clip_local)
+                        p.clip_pos = -1.0 if clip_pos is None else float(clip_pos)
+                        p.seed = seed
+                        p.step_offset = s0
+                        p.noise = _ptr(noise_c[s0:s1]) if noise_c is not None else None
+                        p.traj = _ptr(tbuf) if tbuf is not None else None
+                        p.use_cuda_graph = 1 if use_graph else 0
+                        nan_step = C.c_int32(-1)
+                        rc = lib.agd_sample(self._native_handle(), nb.handle, _ptr(pos_c), C.byref(p), C.byref(nan_step),
+                                            self._stream())
+                        if rc == _lib.AGD_ERR_NAN:
+                            print("NaN detected. Please restart.")
+                            raise FloatingPointError()
+                        _lib.check(rc)
+                        if tbuf is not None:
+                            traj_host[s0:s1, a0:a1].copy_(tbuf[: s1 - s0], non_blocking=True)
+                            torch.cuda.current_stream(dev).synchronize()
+                finally:
+                    nb.close()
         pos_traj: List[torch.Tensor] = list(traj_host.unbind(0)) if traj_host is not None else []
         return pos, pos_traj
 

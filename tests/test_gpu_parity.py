@@ -310,6 +310,10 @@ def test_sampler_properties():
                                                  bt[ecut:].to(DEV), (b[cut:] - half).to(DEV), G - half, seed=11,
                                                  mol_gid=gid[half:], **kw)
     assert torch.equal(torch.cat([pa, pb]), p1)
+    # automatic chunking of large batches is exact as well (several chunks of a few molecules each) and keeps pos_traj
+    kw2 = dict(kw, return_traj=True)
+    p5, t5 = m.langevin_dynamics_sample_diffusion(*args, seed=11, max_chunk_edges=4000, **kw2)
+    assert torch.equal(p5, p1) and len(t5) == 20 and torch.equal(t5[-1], p1.cpu())
 
 
 def test_device_noise_statistics():
