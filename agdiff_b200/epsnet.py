@@ -410,8 +410,13 @@ class DualEncoderEpsNetwork(nn.Module):
 
     def _renorm_embedding(self, atom_type):
         # side effect of nn.Embedding(max_norm=10) in the reference (schnet.py:254,271)
+        # (only when a looked-up row really exceeds the norm: an unconditional in-place call would bump the parameter's
+        # version every time and force a full re-pack + upload of the weights on every forward / sampler call)
         with torch.no_grad():
-            torch.embedding_renorm_(self.encoder_global.embedding.weight, atom_type.contiguous(), 10.0, 2.0)
+            w = self.encoder_global.embedding.weight
+            used = torch.unique(atom_type)
+            if bool((w[used].norm(dim=1) > 10.0).any()):
+                torch.embedding_renorm_(w, used.contiguous(), 10.0, 2.0)
 
     # ------------------------------------------------------------------ forward
     def forward(self, atom_type, pos, bond_index, bond_type, batch, time_step, edge_index=None, edge_type=None,

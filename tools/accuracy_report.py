@@ -35,6 +35,21 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
                 key.split("_")[-1], float((ours - r32).abs().max()) / s, float((ours - r64).abs().max()) / s,
                 float((r32 - r64).abs().max()) / s, s))
         print(" | ".join(row))
+    from util import kabsch_free_rmsd
+    for name in ["traj_alanine2_high", "traj_alanine2_low", "traj_qm9x6_low_smooth"]:
+        g = golden(name)
+        m = make_model(g["cfg_name"], g["seed"], 0).to("cuda:0")
+        d = "cuda:0"
+        n = g["n_steps"]
+        noise = torch.randn(n, g["atom_type"].numel(), 3, generator=torch.Generator().manual_seed(g["noise_seed"]))
+        pos, traj = m.langevin_dynamics_sample_diffusion(
+            g["atom_type"].to(d), g["pos_init"].to(d), g["bond_index"].to(d), g["bond_type"].to(d), g["batch"].to(d),
+            int(g["batch"].max()) + 1, extend_order=False, n_steps=n, step_lr=1e-6, clip=1000.0, clip_local=g["clip_local"],
+            global_start_sigma=g["global_start_sigma"], w_global=g["w_global"], noise=noise, t_start=g["t_start"],
+            scale_init=g["scale_init"])
+        r = kabsch_free_rmsd(pos, g["pos_final"], g["batch"])
+        print("%s: %d steps, max per-molecule RMSD vs the reference's trajectory %.2e A (|pos|max %.1f A)" % (
+            name, n, float(r.max()), float(g["pos_final"].abs().max())))
 else:
     for tc in ("1", "0"):
         print("== AGD_TC_FILTERS=%s (%s)" % (tc, "tcgen05 3xTF32" if tc == "1" else "fp32 FFMA"))
