@@ -392,6 +392,38 @@ def test_op_eq_transform():
     assert_close(out, ref, rtol=1e-4, atol_scale=1e-5, what="eq_transform")
 
 
+# ------------------------------------------------------------------------------- degenerate inputs
+def test_degenerate_batches():
+    """single-atom molecules, molecules without bonds, and geometries with no edge at all (empty tensors, like the reference)"""
+    from agdiff_b200.synth import Molecule
+    m, sd = _cuda_model("qm9", 2021, 0)
+    cfg = CONFIGS["qm9"]
+    lone = Molecule(np.array([6], np.int64), np.zeros((2, 0), np.int64), np.zeros(0, np.int64))
+    pair_nobond = Molecule(np.array([8, 1], np.int64), np.zeros((2, 0), np.int64), np.zeros(0, np.int64))
+    ala = graph.extend_bond_order_host(synth.alanine_dipeptide())
+    # (a) mixed batch: lone atom + unbonded pair within the cutoff + a normal molecule
+    z, bi, bt, b, G = graph.collate([lone, pair_nobond, ala], 1)
+    pos = torch.randn(z.numel(), 3, generator=torch.Generator().manual_seed(0)) * 2.0
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, z, pos, bi, bt, b, extend_order=False)
+    out = m(z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), None, return_edges=True, extend_order=False)
+    assert torch.equal(out[2].cpu(), ref[2]) and torch.equal(out[3].cpu(), ref[3])
+    assert_close(out[0], ref[0], what="edge_inv_global", extra_atol=1e-6)
+    assert_close(out[1], ref[1], what="edge_inv_local", extra_atol=1e-4)
+    # (b) no edge at all: unbonded atoms farther apart than the cutoff -> empty outputs, sampler still steps (pure noise + centring)
+    z, bi, bt, b, G = graph.collate([pair_nobond, lone], 1)
+    pos = torch.tensor([[0.0, 0, 0], [50.0, 0, 0], [0.0, 0, 0]])
+    out = m(z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), None, return_edges=True, extend_order=False)
+    assert out[0].shape == (0, 1) and out[1].shape == (0, 1) and out[2].shape == (2, 0) and out[5].shape == (0,)
+    noise = torch.randn(3, 3, 3, generator=torch.Generator().manual_seed(1))
+    kw = dict(extend_order=False, n_steps=3, step_lr=1e-6, clip=1000.0, clip_local=20.0, global_start_sigma=0.5, w_global=1.0,
+              noise=noise, t_start=2013, scale_init=False)
+    p, traj = m.langevin_dynamics_sample_diffusion(z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), G, **kw)
+    with torch.no_grad():
+        pr, _ = O.sample(sd, cfg, z, pos, bi, bt, b, G, keep_traj=False, **kw)
+    assert float((p.cpu() - pr).abs().max()) < 1e-5 and len(traj) == 3
+
+
 # ------------------------------------------------------------------------------- full-size properties
 def test_full_size_batch_properties():
     """BASELINE-sized batch (1024 QM9-shaped molecules x 2 / 300 Drugs-shaped incl. 181 atoms): properties that do not
