@@ -329,6 +329,7 @@ def run_ours(args):
                                        "costs 3 TF32 MMAs per product and kind::tf32 runs at half the bf16 rate, so the "
                                        "attainable ceiling for this kernel is peak/6",
                         "achieved_tensor_tflops_tf32_issued": round(3 * ach, 3),
+                        "attainable_peak": round(peak / 6, 1), "frac_of_attainable": round(ach / (peak / 6), 4),
                         "dominant_by_time": top}
             ag_ms, ag_n = per_kernel.get("schnet.aggregate", (0.0, 1))
             if ag_ms > 0:
