@@ -12,7 +12,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libagdiff_b200.so")
 
-AGD_OK, AGD_ERR_INVALID, AGD_ERR_CUDA, AGD_ERR_CAPACITY, AGD_ERR_NAN = 0, -1, -2, -3, -4
+AGD_OK, AGD_ERR_INVALID, AGD_ERR_CUDA, AGD_ERR_CAPACITY, AGD_ERR_NAN, AGD_ERR_RANGE = 0, -1, -2, -3, -4, -5
+MODE_FFMA, MODE_TF32, MODE_F16 = 0, 1, 2
 MAX_MOL_ATOMS = 256
 MAX_RADIUS_NBRS = 32
 
@@ -22,6 +23,7 @@ EXPORTS = [
     "agd_batch_create", "agd_batch_destroy", "agd_build_edges", "agd_forward", "agd_sample",
     "agd_extend_bond_order", "agd_op_cfconv_aggregate", "agd_op_eq_transform", "agd_debug_fetch",
     "agd_launch_count", "agd_profile_forward", "agd_forward_edges",
+    "agd_set_mode", "agd_get_mode", "agd_set_option", "agd_range_flag", "agd_f16_lo_shift",
 ]
 
 
@@ -109,6 +111,11 @@ def load() -> C.CDLL:
     lib.agd_profile_forward.argtypes = [vp, vp, vp, i32, C.c_char_p, i64, vp, i32, C.POINTER(i32), C.POINTER(i32), vp]
     lib.agd_launch_count.argtypes = [vp]
     lib.agd_launch_count.restype = i64
+    lib.agd_set_mode.argtypes = [vp, C.c_int]
+    lib.agd_get_mode.argtypes = [vp]
+    lib.agd_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.agd_range_flag.argtypes = [vp, C.POINTER(i32)]
+    lib.agd_f16_lo_shift.restype = C.c_int
     if lib.agd_abi_version() != 1:
         raise ImportError("libagdiff_b200.so ABI version mismatch")
     _lib = lib

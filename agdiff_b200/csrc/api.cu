@@ -18,6 +18,7 @@ void set_gin_attributes();
 void set_tc_attributes();
 void set_tc_mlp_attributes();
 void set_tc_node_attributes();
+void set_tc16_attributes();
 }  // namespace agd
 
 using namespace agd;
@@ -50,7 +51,9 @@ struct agd_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   int64_t launches = 0;
-  int use_tc = 1;
+  int f16_fuse = 1;
+  int f16_debug_filt = 0;
+  int use_tc = 2;   // AGD_TC_FILTERS / agd_set_mode: 0 FFMA, 1 tcgen05 3xTF32, 2 tcgen05 + 3xFP16 filter kernels
 };
 
 struct agd_batch {
@@ -100,6 +103,9 @@ static void build_slots(agd_handle* h) {
     add(p + "tL2a", 2 * 128 * 128, &b.tL2a); add(p + "tL2b", 2 * 128 * 64, &b.tL2b);
     add(p + "tLINa", 2 * 128 * 128, &b.tLINa); add(p + "tLINb", 2 * 128 * 128, &b.tLINb);
     add(p + "tA1", 2 * 64 * 128, &b.tA1);
+    add(p + "hF1a", 128 * 128, &b.hF1a); add(p + "hF2a", 128 * 128, &b.hF2a);
+    add(p + "hF1b", 64 * 128, &b.hF1b);   add(p + "hF2b", 64 * 64, &b.hF2b);
+    add(p + "hsc", 4, &b.hsc);
   }
   auto add_pair = [&](const std::string& p, PairW& q) {
     add(p + "P1h", H * H, &q.P1h); add(p + "P1e", H * H, &q.P1e); add(p + "p1b", H, &q.p1b);
@@ -126,6 +132,8 @@ static LaunchCtx make_ctx(agd_handle* h) {
   c.launch_counter = &h->launches;
   c.prof = nullptr;
   c.use_tc = h->use_tc;
+  c.f16_fuse = h->f16_fuse;
+  c.f16_debug_filt = h->f16_debug_filt;
   c.cutoff = h->cfg.cutoff;
   c.smooth = h->cfg.smooth_conv;
   c.num_convs = h->cfg.num_convs;
@@ -169,7 +177,7 @@ static void run_global_branch(const LaunchCtx& c, const BatchDev& b, const Model
   if (c.use_tc) launch_schnet_node_tc(c, b, w, -1); else launch_schnet_node(c, b, w, -1);
   for (int k = 0; k < c.num_convs; ++k) {
     launch_filters(c, b, w, k);
-    if (!(c.use_tc && filters_tc_fused())) launch_aggregate(c, b.xcat, b.filt, b.e_src, b.in_ptr, b.n_atoms, 192, b.agg);
+    if (!((c.use_tc == 1 && filters_tc_fused()) || (c.use_tc == 2 && c.f16_fuse))) launch_aggregate(c, b.xcat, b.filt, b.e_src, b.in_ptr, b.n_atoms, 192, b.agg);
     if (c.use_tc) launch_schnet_node_tc(c, b, w, k); else launch_schnet_node(c, b, w, k);
   }
   if (c.use_tc) launch_pair_global_tc(c, b, w); else launch_pair_global(c, b, w);
@@ -205,7 +213,9 @@ int agd_create(const agd_config* cfg, agd_handle** out) {
   set_tc_attributes();
   set_tc_mlp_attributes();
   set_tc_node_attributes();
-  if (const char* e = std::getenv("AGD_TC_FILTERS")) h->use_tc = (e[0] != '0');
+  set_tc16_attributes();
+  h->f16_fuse = f16_fuse_default();
+  if (const char* e = std::getenv("AGD_TC_FILTERS")) h->use_tc = (e[0] == '0') ? 0 : (e[0] == '1') ? 1 : 2;
   CUDA_TRY(cudaGetLastError());
   *out = h;
   return AGD_OK;
@@ -292,6 +302,7 @@ static void carve(BatchDev& d, Carver& c) {
   d.sl_canon = c.take<float>(L);
   d.ea_loc = c.take<float>(L * HID);
   d.g2 = c.take<float>(E * HID);
+  d.g2h = c.take<uint4>(((E + TM - 1) / TM) * TM * (HID / 4));
   d.filt = c.take<float>(E * 192);
   d.h = c.take<float>(N * HID);
   d.xcat = c.take<float>(N * 192);
@@ -397,6 +408,7 @@ int agd_forward(agd_handle* h, agd_batch* b, const float* pos, const agd_forward
   if (!pos || !out) return fail(AGD_ERR_INVALID, "null argument");
   if ((rc = enter(h, stream))) return rc;
   LaunchCtx c = make_ctx(h);
+  CUDA_TRY(cudaMemsetAsync(b->d.counters + 4, 0, sizeof(int), h->stream));
   run_global_branch(c, b->d, h->w, pos);
   run_local_branch(c, b->d, h->w, pos, nullptr);
   launch_export_edges(c, b->d, *out, true);
@@ -419,6 +431,7 @@ int agd_forward_edges(agd_handle* h, agd_batch* b, const float* pos, const agd_e
   CUDA_TRY(cp(d.c_len, es->c_len, E * 4));
   const int n = es->n_edges;
   CUDA_TRY(cudaMemcpyAsync(d.counters, &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemsetAsync(d.counters + 4, 0, sizeof(int), h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));   // `n` lives on this stack frame
   LaunchCtx c = make_ctx(h);
   run_global_branch(c, d, h->w, pos, /*build=*/false);
@@ -452,7 +465,7 @@ int agd_sample(agd_handle* h, agd_batch* b, float* pos, const agd_sample_params*
     sched[4 * s + 3] = p->use_global[s] ? 1.f : 0.f;
   }
   CUDA_TRY(cudaMemcpyAsync(d.sched, sched.data(), sizeof(float) * sched.size(), cudaMemcpyHostToDevice, h->stream));
-  const int init[4] = {0, 0, INT_MAX, 0};
+  const int init[5] = {0, 0, INT_MAX, 0, 0};
   CUDA_TRY(cudaMemcpyAsync(d.counters, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));  // `sched`/`init` are stack/heap temporaries
 
@@ -507,6 +520,12 @@ int agd_sample(agd_handle* h, agd_batch* b, float* pos, const agd_sample_params*
   }
   CUDA_TRY(cudaGetLastError());
   if ((rc = check_overflow(b))) return rc;
+  int range_flag = 0;
+  CUDA_TRY(cudaMemcpy(&range_flag, d.counters + 4, sizeof(int), cudaMemcpyDeviceToHost));
+  if (range_flag) {
+    if ((rc = leave(h, stream))) return rc;
+    return fail(AGD_ERR_RANGE, "an activation left the fp16-split range; re-run in AGD_MODE_TF32");
+  }
   int nan_step = INT_MAX;
   CUDA_TRY(cudaMemcpy(&nan_step, d.counters + 2, sizeof(int), cudaMemcpyDeviceToHost));
   if ((rc = leave(h, stream))) return rc;
@@ -538,6 +557,8 @@ int agd_op_cfconv_aggregate(const float* x, const float* W, const int32_t* src, 
   c.launch_counter = &dummy;
   c.prof = nullptr;
   c.use_tc = 0;
+  c.f16_fuse = 0;
+  c.f16_debug_filt = 0;
   launch_aggregate(c, x, W, src, in_ptr, n_nodes, F, out);
   CUDA_TRY(cudaGetLastError());
   return AGD_OK;
@@ -577,6 +598,28 @@ int64_t agd_debug_fetch(agd_batch* b, const char* name, float* dst, int64_t capa
 }
 
 int64_t agd_launch_count(const agd_handle* h) { return h ? h->launches : 0; }
+
+int agd_set_mode(agd_handle* h, int mode) {
+  if (!h || mode < AGD_MODE_FFMA || mode > AGD_MODE_F16) return fail(AGD_ERR_INVALID, "mode must be 0, 1 or 2");
+  h->use_tc = mode;
+  return AGD_OK;
+}
+int agd_get_mode(const agd_handle* h) { return h ? h->use_tc : AGD_ERR_INVALID; }
+int agd_set_option(agd_handle* h, const char* name, int value) {
+  if (!h || !name) return fail(AGD_ERR_INVALID, "null argument");
+  if (std::strcmp(name, "f16_fuse") == 0) h->f16_fuse = value ? 1 : 0;
+  else if (std::strcmp(name, "f16_debug_filt") == 0) h->f16_debug_filt = value ? 1 : 0;
+  else return fail(AGD_ERR_INVALID, std::string("unknown option ") + name);
+  return AGD_OK;
+}
+int agd_f16_lo_shift(void) { return f16_lo_shift(); }
+int agd_range_flag(agd_batch* b, int32_t* flag_out) {
+  if (!b || !flag_out) return fail(AGD_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(b->h->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(b->h->stream));
+  CUDA_TRY(cudaMemcpy(flag_out, b->d.counters + 4, sizeof(int), cudaMemcpyDeviceToHost));
+  return AGD_OK;
+}
 
 int agd_profile_forward(agd_handle* h, agd_batch* b, const float* pos, int32_t with_global, char* labels, int64_t labels_cap,
                         float* ms, int32_t cap, int32_t* n_out, int32_t* n_edges_out, void* stream) {

@@ -33,6 +33,8 @@ struct BlkW {              // InteractionBlock k, schnet.py:165-216 (+ scaling m
   const float *sc;                           // scalars: beta(conv1.nn.1), beta(conv2.nn.1), beta(act), attention.2.bias
   const float *tF1a, *tF2a, *tF1b, *tF2b;    // tcgen05 operand images of the filter nets: [hi | lo], K-major SWIZZLE_128B
   const float *tL1a, *tL1b, *tL2a, *tL2b, *tLINa, *tLINb, *tA1;   // ... of the node-side Linears
+  const float *hF1a, *hF2a, *hF1b, *hF2b;    // fp16-split operand images of the filter nets: [hi | lo'] packed halves (tc_filter16.cu)
+  const float* hsc;                          // inverse power-of-two weight scales of hF1a, hF2a, hF1b, hF2b
 };
 struct PairW {             // grad_{global,local}_dist_mlp, common.py:86-103 on [h_row*h_col, edge_attr]
   const float *P1h, *P1e, *p1b;   // layers.0 split: [128][128] on h_row*h_col, [128][128] on g2 (global, merged) / edge_attr (local)
@@ -84,6 +86,7 @@ struct BatchDev {
   float* ea_loc;                 // [n_local][128]
   // activations
   float* g2;                     // [cap][128]  encoder hidden state feeding filters and the pair MLP
+  uint4* g2h;                    // [ceil(cap/128)*128][128 words] fp16-split copy of g2 (AGD_MODE_F16; layout: g2h_index in tc_common.cuh)
   float* filt;                   // [cap][192]  CFConv filters of the current block (conv1 | conv2)
   float *h, *xcat, *agg;         // [N][128], [N][192], [N][192]
   float *gx0, *gx1;              // [N][128] GIN ping-pong
@@ -112,7 +115,9 @@ struct LaunchCtx {
   int num_sms;
   int64_t* launch_counter;
   Prof* prof;
-  int use_tc;      // 1: CFConv filter nets on tcgen05 (3xTF32), 0: fp32 FFMA tile kernels
+  int use_tc;      // 0: fp32 FFMA tile kernels, 1: tcgen05 3xTF32 everywhere, 2: tcgen05 with 3xFP16 two-slot filter kernels
+  int f16_debug_filt;   // fused kernels also write the filter tensor
+  int f16_fuse;    // use_tc == 2: CFConv aggregation fused into the filter kernels (no filt tensor, no aggregate kernel)
   float cutoff;
   int smooth;
   int num_convs, num_convs_local;
@@ -132,6 +137,9 @@ void launch_pair_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w, c
 // schnet.cu
 void launch_filters(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);
 void launch_filters_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);   // tc_filter.cu
+void launch_filters_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);  // tc_filter16.cu
+int f16_lo_shift();   // S of the fp16 lo' = (x - hi) * 2^S split (0: unscaled), pack.py must build the weight images with it
+int f16_fuse_default();    // AGD_F16_FUSE (default 1): launch_filters_f16 also performs the CFConv aggregation into agg
 bool filters_tc_fused();   // true: launch_filters_tc also performs the CFConv aggregation into agg
 // tc_mlp.cu
 void launch_encoder_global_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w);

@@ -249,6 +249,10 @@ static int tiles_grid(int64_t rows_cap, int num_sms, int per_sm) {
 }
 
 void launch_filters(const LaunchCtx& c, const BatchDev& b, const ModelW& mw, int blk) {
+  if (c.use_tc == 2) {
+    launch_filters_f16(c, b, mw, blk);
+    return;
+  }
   if (c.use_tc) {
     launch_filters_tc(c, b, mw, blk);
     return;

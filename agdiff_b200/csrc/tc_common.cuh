@@ -1,6 +1,8 @@
 // tcgen05 / TMEM / mbarrier / bulk-copy primitives shared by the tensor-core kernels (sm_100a inline PTX;
 // spellings follow the CUTLASS/CuTe sm100 headers, descriptor bit layouts cute::UMMA::{SmemDescriptor,InstrDescriptor}).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace agd {
@@ -185,6 +187,25 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
   const float rem = v - __uint_as_float(hi);
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rem));
+}
+
+// ---- fp16 split ("3xFP16", tc_filter16.cu): two fp32 values -> packed fp16 hi pair and packed fp16 lo' pair
+// (low half = first value), hi = rn_f16(x), lo' = rn_f16((x - hi) * lo_scale); amax tracks max|x| for the range check.
+constexpr int F16_LO_SHIFT = 11;        // S: lo' = (x - hi) * 2^S (pack.umma_image_f16 builds the weight images with it)
+constexpr float F16_RANGE = 65000.f;
+__device__ __forceinline__ void split2_f16(float x0, float x1, float lo_scale, uint32_t& hi, uint32_t& lo, float& amax) {
+  amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((x0 - hf.x) * lo_scale, (x1 - hf.y) * lo_scale);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// The pre-split copy of the encoder state g2 that the fp16 filter kernels read ("g2h"): per 128-edge block
+// [word quad w4 (32)][row (128)][4 words], words 0..63 of a row = packed hi pairs of features (2w, 2w+1), words 64..127 the
+// lo' pairs.  Producer and consumers are thread-per-row, so every warp access is 512 contiguous bytes.
+__device__ __forceinline__ size_t g2h_index(int64_t row, int w4) {   // in uint4 units
+  return (static_cast<size_t>(row >> 7) * 32 + w4) * 128 + static_cast<size_t>(row & 127);
 }
 
 }  // namespace agd

@@ -85,6 +85,9 @@ struct TcEncArgs {
   float *len_csc, *len_canon;
   const float* len_in;            // local: caller-supplied lengths instead of |pos[src]-pos[dst]|
   float* out;                     // g2 (global) / edge_attr (local) [rows][128]
+  uint4* g2h;                     // global, AGD_MODE_F16: pre-split fp16 copy of g2 for the filter kernels (layout: g2h_index)
+  float lo_scale;                 // 2^S of the lo' part
+  int* range_flag;                // set when |g2| leaves the fp16-split range
 };
 
 constexpr size_t TC_ENC_SMEM = 1024 + 131072 + 4 * 128 * sizeof(float) + 256;
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) tc_encoder_kernel(const TcEncA
       else if (more) cx.stream(a.tW1, IMG128);
     }
     // ---- g2 = gelu(D + T2[type])
+    float amax = 0.f;
     const float* T2 = a.w.T2 + type * HID;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -211,8 +215,19 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) tc_encoder_kernel(const TcEncA
         float4* dst = reinterpret_cast<float4*>(a.out + r * HID + n0);
 #pragma unroll
         for (int q = 0; q < 4; ++q) dst[q] = make_float4(t[q * 4], t[q * 4 + 1], t[q * 4 + 2], t[q * 4 + 3]);
+        if (a.g2h) {   // the same 16 features as packed fp16 hi / lo' pairs: words n0/2 .. n0/2+7 of the row and of its lo' half
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split2_f16(t[2 * j], t[2 * j + 1], a.lo_scale, hi[j], lo[j], amax);
+          const int w4 = n0 >> 3;
+          a.g2h[g2h_index(r, w4)] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          a.g2h[g2h_index(r, w4 + 1)] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          a.g2h[g2h_index(r, 16 + w4)] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          a.g2h[g2h_index(r, 16 + w4 + 1)] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        }
       }
     }
+    if (!LOCAL && amax > F16_RANGE) atomicOr(a.range_flag, 1);
     if (LOCAL) {
       cx.layer_streamed(128, 128, false);               // combination_mlp.2
       cx.wait_mma();
@@ -408,6 +423,11 @@ void launch_encoder_global_tc(const LaunchCtx& c, const BatchDev& b, const Model
   a.w = w.enc; a.tW1 = w.tenc_W1; a.tM2 = w.tenc_M2; a.tC2 = w.tenc_C2;
   a.n_rows_dev = b.counters;
   a.e_len = b.e_len; a.e_type = b.e_type; a.out = b.g2;
+  if (c.use_tc == 2) {
+    a.g2h = b.g2h;
+    a.lo_scale = static_cast<float>(1 << f16_lo_shift());
+    a.range_flag = b.counters + 4;
+  }
   tc_encoder_kernel<false><<<tc_grid(b.cap, c.num_sms), TCM_THREADS, TC_ENC_SMEM, c.stream>>>(a);
   note_launch(c, "encoder.global_tc");
 }

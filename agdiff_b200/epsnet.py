@@ -350,10 +350,42 @@ class DualEncoderEpsNetwork(nn.Module):
         n = lib.agd_weight_slot_count(h)
         names = [lib.agd_weight_slot_name(h, i).decode() for i in range(n)]
         sizes = [int(lib.agd_weight_slot_size(h, i)) for i in range(n)]
-        folded = fold_state_dict(self.state_dict(), int(self.config.num_convs), int(self.config.num_convs_local))
+        folded = fold_state_dict(self.state_dict(), int(self.config.num_convs), int(self.config.num_convs_local),
+                                 lo_shift=int(lib.agd_f16_lo_shift()))
         buf, offs = pack(folded, names, sizes)
         _lib.check(lib.agd_load_weights(h, buf.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), n, buf.size))
         self._packed_version = ver
+
+    def _range_exceeded(self, nb) -> bool:
+        """True when the last forward on this batch met an activation outside the fp16-split range (AGD_MODE_F16 only)."""
+        lib = _lib.load()
+        if lib.agd_get_mode(self._native_handle()) != _lib.MODE_F16:
+            return False
+        flag = C.c_int32(0)
+        _lib.check(lib.agd_range_flag(nb.handle, C.byref(flag)))
+        return bool(flag.value)
+
+    def _mode(self, mode):
+        """context manager: run the enclosed native calls with another arithmetic mode (see agd_set_mode)."""
+        model, lib = self, _lib.load()
+
+        class _Ctx:
+            def __enter__(self):
+                self.prev = lib.agd_get_mode(model._native_handle())
+                _lib.check(lib.agd_set_mode(model._native_handle(), int(mode)))
+
+            def __exit__(self, *exc):
+                _lib.check(lib.agd_set_mode(model._native_handle(), self.prev))
+                return False
+        return _Ctx()
+
+    def set_mode(self, mode: int) -> None:
+        """0: fp32 FFMA kernels, 1: tcgen05 3xTF32, 2: tcgen05 with fp16-split two-slot filter kernels (default)."""
+        _lib.check(_lib.load().agd_set_mode(self._native_handle(), int(mode)))
+
+    def set_option(self, name: str, value: int) -> None:
+        """native tuning / A-B switches (agd_set_option), e.g. ("f16_fuse", 0)."""
+        _lib.check(_lib.load().agd_set_option(self._native_handle(), name.encode(), int(value)))
 
     def launch_count(self) -> int:
         return int(_lib.load().agd_launch_count(self._native_handle()))
@@ -452,6 +484,9 @@ class DualEncoderEpsNetwork(nn.Module):
         out = _lib.ForwardOut(_ptr(eg), _ptr(el), _ptr(erow), _ptr(ecol), _ptr(etyp), _ptr(elen), _ptr(ne))
         fn = lib.agd_build_edges if build_only else lib.agd_forward
         _lib.check(fn(self._native_handle(), nb.handle, _ptr(pos), C.byref(out), self._stream()))
+        if not build_only and self._range_exceeded(nb):
+            with self._mode(_lib.MODE_TF32):     # fp16-split range left: same call on the 3xTF32 kernels
+                _lib.check(fn(self._native_handle(), nb.handle, _ptr(pos), C.byref(out), self._stream()))
         E = int(ne.item())
         if E > nb.cap:
             raise RuntimeError("edge count %d exceeded the planned capacity %d" % (E, nb.cap))
@@ -502,6 +537,10 @@ class DualEncoderEpsNetwork(nn.Module):
             out = _lib.ForwardOut(_ptr(eg), _ptr(el), None, None, None, None, None)
             torch.cuda.synchronize(dev)
             _lib.check(lib.agd_forward_edges(self._native_handle(), nb.handle, _ptr(pos), C.byref(es), C.byref(out), self._stream()))
+            if self._range_exceeded(nb):
+                with self._mode(_lib.MODE_TF32):
+                    _lib.check(lib.agd_forward_edges(self._native_handle(), nb.handle, _ptr(pos), C.byref(es), C.byref(out),
+                                                     self._stream()))
             torch.cuda.current_stream(dev).synchronize()
         finally:
             nb.close()
@@ -629,8 +668,15 @@ class DualEncoderEpsNetwork(nn.Module):
                         p.traj = _ptr(tbuf) if tbuf is not None else None
                         p.use_cuda_graph = 1 if use_graph else 0
                         nan_step = C.c_int32(-1)
+                        f16 = lib.agd_get_mode(self._native_handle()) == _lib.MODE_F16
+                        backup = pos_c.clone() if f16 else None      # the span is re-run on the 3xTF32 kernels if needed
                         rc = lib.agd_sample(self._native_handle(), nb.handle, _ptr(pos_c), C.byref(p), C.byref(nan_step),
                                             self._stream())
+                        if rc == _lib.AGD_ERR_RANGE:
+                            pos_c.copy_(backup)
+                            with self._mode(_lib.MODE_TF32):
+                                rc = lib.agd_sample(self._native_handle(), nb.handle, _ptr(pos_c), C.byref(p), C.byref(nan_step),
+                                                    self._stream())
                         if rc == _lib.AGD_ERR_NAN:
                             print("NaN detected. Please restart.")
                             raise FloatingPointError()

@@ -59,8 +59,32 @@ def umma_image(W: np.ndarray) -> np.ndarray:
     return out
 
 
-def fold_state_dict(sd: Dict[str, torch.Tensor], num_convs: int, num_convs_local: int) -> Dict[str, np.ndarray]:
-    """-> {slot name: float64 array}."""
+def umma_image_f16(W: np.ndarray, lo_shift: int = 11):
+    """tcgen05 kind::f16 B-operand image of a Linear weight W[N][K] for the fp16-split kernels (csrc/tc_filter16.cu).
+    The fp32 weight is scaled by a power of two s (max|w|*s in [2^13, 2^14): every part stays a NORMAL fp16 number for
+    weights down to 2^-17 of the largest) and split into hi = rn_f16(w*s), lo' = rn_f16((w*s - hi) * 2^lo_shift); each
+    part is laid out K-major SWIZZLE_128B: K in atoms of 64 halves (128 B rows), per atom N rows of 128 B, 16-byte
+    chunk c of row n stored at chunk c ^ (n % 8).  Returns ([hi image | lo' image] as float32 bit patterns, 1/s)."""
+    w32 = np.ascontiguousarray(W, dtype=np.float64).astype(np.float32)
+    N, K = w32.shape
+    assert K % 64 == 0 and N % 8 == 0
+    m = float(np.abs(w32).max())
+    e = 0 if not np.isfinite(m) or m == 0.0 else 13 - int(np.floor(np.log2(m)))
+    e = max(-100, min(100, e))
+    ws = np.ldexp(w32, e).astype(np.float32)                 # exact (power of two)
+    hi = ws.astype(np.float16)
+    lo = np.ldexp(ws - hi.astype(np.float32), lo_shift).astype(np.float16)
+    n = np.arange(N)[:, None]
+    k = np.arange(K)[None, :]
+    off = (k // 64) * (N * 64) + n * 64 + ((((k % 64) // 8) ^ (n % 8)) * 8) + (k % 8)
+    img = np.zeros(2 * N * K, dtype=np.float16)
+    img[off.reshape(-1)] = hi.reshape(-1)
+    img[N * K + off.reshape(-1)] = lo.reshape(-1)
+    return img.view(np.float32).copy(), float(np.ldexp(1.0, -e))
+
+
+def fold_state_dict(sd: Dict[str, torch.Tensor], num_convs: int, num_convs_local: int, lo_shift: int = 11) -> Dict[str, np.ndarray]:
+    """-> {slot name: float64 array} (operand images: float32 bit patterns)."""
     out: Dict[str, np.ndarray] = {}
     e = "edge_encoder_global."
     bond = _f64(sd[e + "bond_emb.weight"])
@@ -110,6 +134,12 @@ def fold_state_dict(sd: Dict[str, torch.Tensor], num_convs: int, num_convs_local
             W, bb = _fold_bn(sd, cp + "lin2", cp + "norm2")
             out[p + "L2" + tag], out[p + "l2%sb" % tag] = W, bb
             out[p + "tL2" + tag] = umma_image(W.T)
+        hsc = np.zeros(4)
+        for j, tag in enumerate(("F1a", "F2a", "F1b", "F2b")):
+            cp = "%sconv%d." % (ip, 1 if tag.endswith("a") else 2)
+            Wm = (_f64(sd[cp + "nn.0.weight"]) @ C2) if tag.startswith("F1") else _f64(sd[cp + "nn.2.weight"])
+            out[p + "h" + tag], hsc[j] = umma_image_f16(Wm, lo_shift)
+        out[p + "hsc"] = hsc
         out[p + "LIN"] = _f64(sd[ip + "lin.weight"]).T
         out[p + "tLINa"] = umma_image(_f64(sd[ip + "lin.weight"])[:, :128])
         out[p + "tLINb"] = umma_image(_f64(sd[ip + "lin.weight"])[:, 128:])
@@ -170,5 +200,9 @@ def pack(folded: Dict[str, np.ndarray], slot_names, slot_sizes, align: int = 32)
         total += (size + align - 1) // align * align
     buf = np.zeros(total, dtype=np.float32)
     for name, size, off in zip(slot_names, slot_sizes, offsets):
-        buf[off:off + size] = np.ascontiguousarray(folded[name], dtype=np.float64).reshape(-1).astype(np.float32)
+        arr = folded[name]
+        if arr.dtype == np.float32:      # operand images are bit patterns: copy them untouched
+            buf[off:off + size] = arr.reshape(-1)
+        else:
+            buf[off:off + size] = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1).astype(np.float32)
     return buf, np.asarray(offsets, dtype=np.int64)

@@ -29,7 +29,9 @@ enum {
   AGD_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
   AGD_ERR_CUDA = -2,      /* CUDA runtime error (text in agd_last_error) */
   AGD_ERR_CAPACITY = -3,  /* a caller-supplied buffer or the workspace is too small */
-  AGD_ERR_NAN = -4        /* NaN positions during sampling (FloatingPointError, dualenc.py:539-541) */
+  AGD_ERR_NAN = -4,       /* NaN positions during sampling (FloatingPointError, dualenc.py:539-541) */
+  AGD_ERR_RANGE = -5      /* an activation left the fp16-split range in AGD_MODE_F16: nothing valid was produced,
+                             re-run the call in AGD_MODE_TF32 (the Python mirror does this automatically) */
 };
 
 typedef struct agd_handle agd_handle;   /* model: configuration + packed device weights */
@@ -185,6 +187,23 @@ int agd_profile_forward(agd_handle* h, agd_batch* b, const float* pos_dev, int32
 
 /* number of kernel launches issued by the library since the handle was created */
 int64_t agd_launch_count(const agd_handle* h);
+
+/* arithmetic of the dense per-edge / per-atom contractions (all fp32-faithful, all on the GPU):
+ *   AGD_MODE_FFMA  fp32 FFMA tile kernels,
+ *   AGD_MODE_TF32  tcgen05 kind::tf32 with the 3xTF32 split (unbounded range),
+ *   AGD_MODE_F16   tcgen05 kind::f16 with the fp16 hi/lo' split in the CFConv filter kernels, two edge tiles in
+ *                  flight per SM (default; activations beyond +-65000 make the call fail with AGD_ERR_RANGE).
+ * The environment variable AGD_TC_FILTERS=0/1/2 selects the initial mode of new handles. */
+enum { AGD_MODE_FFMA = 0, AGD_MODE_TF32 = 1, AGD_MODE_F16 = 2 };
+int agd_set_mode(agd_handle* h, int mode);
+int agd_get_mode(const agd_handle* h);
+/* tuning / A-B switches.  "f16_fuse" (default 1, env AGD_F16_FUSE): in AGD_MODE_F16 the CFConv aggregation runs inside the
+ * filter kernels (same sums in the same order as the stand-alone aggregate kernel, bit for bit). */
+int agd_set_option(agd_handle* h, const char* name, int value);
+/* 1 if a kernel of the last forward on this batch saw an activation outside the fp16-split range (host sync) */
+int agd_range_flag(agd_batch* b, int32_t* flag_out);
+/* S of the fp16 split lo' = (x - hi) * 2^S the library was built/configured with; the packer builds the images with it */
+int agd_f16_lo_shift(void);
 
 #ifdef __cplusplus
 }

@@ -347,6 +347,84 @@ def test_nan_raises_floating_point_error():
                                              global_start_sigma=0.5, w_global=1.0, seed=3)
 
 
+def _fwd_mode(m, mode, z, pos, bi, bt, b, fetch=("filt", "agg", "h_global")):
+    """forward in one arithmetic mode (0 FFMA, 1 3xTF32, 2 fp16-split filters) + a few internal tensors"""
+    m.set_mode(mode)
+    m._renorm_embedding(z.to(DEV))
+    m._sync_weights()
+    nb = m._prepare(z.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), False)
+    try:
+        res = m._forward_native(nb, pos.to(DEV))
+        E, N = res[2].shape[1], z.numel()
+        inner = {}
+        for name in fetch:
+            n = E * 192 if name == "filt" else N * (128 if name == "h_global" else 192)
+            inner[name] = nb.fetch(name, n).cpu()
+    finally:
+        nb.close()
+    return res, inner
+
+
+@pytest.mark.parametrize("kind,cfg_name,scale", [("drugs", "drugs", 2.5), ("qm9", "qm9", 2.0), ("drugs", "drugs", 0.7)])
+def test_f16_split_filters_match_tf32_and_ffma(kind, cfg_name, scale):
+    """The fp16-split (kind::f16, two tiles in flight) filter kernels against the 3xTF32 and FFMA kernels on the same
+    input: the last block's filter tensor, its aggregate and the node state agree to fp32-noise level."""
+    m, sd = _cuda_model(cfg_name, 2021, 5)
+    z, bi, bt, b, G, pos = _batch(kind, seed=11, scale=scale)
+    m.set_option("f16_fuse", 0)          # keep the filter tensor in HBM for the comparison (fused: next test)
+    r2, i2 = _fwd_mode(m, 2, z, pos, bi, bt, b)
+    m.set_option("f16_fuse", 1)
+    r1, i1 = _fwd_mode(m, 1, z, pos, bi, bt, b)
+    r0, i0 = _fwd_mode(m, 0, z, pos, bi, bt, b)
+    m.set_mode(2)
+    assert torch.equal(r2[2], r1[2])
+    for name in ("filt", "agg", "h_global"):
+        e21, e10 = rel_err(i2[name], i0[name]), rel_err(i1[name], i0[name])
+        assert e21 < 2e-5 and e21 < 4 * e10 + 2e-6, "%s: f16-split vs FFMA %.2e, 3xTF32 vs FFMA %.2e" % (name, e21, e10)
+    for k in (0, 1):
+        assert_close(r2[k], r0[k], what="f16 vs ffma output %d" % k)
+
+
+@pytest.mark.parametrize("kind,cfg_name,scale,repeats", [("drugs", "drugs", 2.5, 3), ("qm9", "qm9", 2.0, 1), ("drugs", "drugs", 6.0, 2)])
+def test_f16_fused_aggregation_bitwise_equals_unfused(kind, cfg_name, scale, repeats):
+    """The aggregation fused into the fp16 filter kernels walks every destination's edges in CSC order with one fmaf per
+    edge - runs cut by a tile boundary are CONTINUED through the carry hand-off, not re-associated - so it equals the
+    stand-alone cfconv_aggregate_kernel on the same filter values bit for bit, wherever tile / CTA boundaries fall."""
+    m, sd = _cuda_model(cfg_name, 2021, 5)
+    _settle(m)
+    z, bi, bt, b, G, pos = _batch(kind, seed=13, scale=scale, repeats=repeats)
+    m.set_option("f16_fuse", 1)
+    rf, inf_ = _fwd_mode(m, 2, z, pos, bi, bt, b, fetch=("agg", "h_global"))
+    m.set_option("f16_fuse", 0)
+    ru, inu = _fwd_mode(m, 2, z, pos, bi, bt, b, fetch=("agg", "h_global"))
+    m.set_option("f16_fuse", 1)
+    assert torch.equal(inf_["agg"], inu["agg"]), "agg differs: max %.3e" % float((inf_["agg"] - inu["agg"]).abs().max())
+    assert torch.equal(inf_["h_global"], inu["h_global"])
+    assert torch.equal(rf[0], ru[0]) and torch.equal(rf[1], ru[1])
+
+
+def test_f16_range_overflow_falls_back_to_tf32():
+    """activations beyond the fp16 range: the fp16-split kernels flag it and the host re-runs the call on the 3xTF32
+    kernels, so the result equals the 3xTF32 result bit for bit (forward and sampler)."""
+    m, sd = _cuda_model("qm9", 2021, 0)
+    with torch.no_grad():   # blow up the first filter layer of block 0 so SSP outputs exceed 65000
+        getattr(m.encoder_global.interactions[0].conv1.nn, "0").weight.mul_(3.0e7)
+    _settle(m)
+    z, bi, bt, b, G, pos = _batch("qm9", seed=4, scale=2.0)
+    r1, _ = _fwd_mode(m, 1, z, pos, bi, bt, b, fetch=())
+    r2, _ = _fwd_mode(m, 2, z, pos, bi, bt, b, fetch=())
+    assert torch.isfinite(r1[0]).all()
+    assert torch.equal(r2[0], r1[0]) and torch.equal(r2[1], r1[1])
+    kw = dict(extend_order=False, n_steps=6, step_lr=1e-6, clip=1000.0, clip_local=20.0, global_start_sigma=float("inf"),
+              w_global=1.0, seed=5, t_start=50, scale_init=False, return_traj=False)
+    outs = []
+    for mode in (1, 2):
+        m.set_mode(mode)
+        p, _ = m.langevin_dynamics_sample_diffusion(z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), G, **kw)
+        outs.append(p.cpu())
+    assert torch.equal(outs[0], outs[1])
+
+
 # ------------------------------------------------------------------------------- stand-alone ops
 @pytest.mark.parametrize("F", [64, 128, 192])
 def test_op_cfconv_aggregate(F):

@@ -51,7 +51,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         print("%s: %d steps, max per-molecule RMSD vs the reference's trajectory %.2e A (|pos|max %.1f A)" % (
             name, n, float(r.max()), float(g["pos_final"].abs().max())))
 else:
-    for tc in ("1", "0"):
-        print("== AGD_TC_FILTERS=%s (%s)" % (tc, "tcgen05 3xTF32" if tc == "1" else "fp32 FFMA"))
-        env = dict(os.environ, AGD_TC_FILTERS=tc)
+    names = {"2": "tcgen05, fp16-split two-slot filter kernels", "1": "tcgen05 3xTF32", "0": "fp32 FFMA"}
+    for tc, extra in (("2", {}), ("2", {"AGD_F16_LOSHIFT": "0"}), ("1", {}), ("0", {})):
+        print("== AGD_TC_FILTERS=%s (%s) %s" % (tc, names[tc], extra or ""))
+        env = dict(os.environ, AGD_TC_FILTERS=tc, **extra)
         subprocess.run([sys.executable, __file__, "child"], env=env, check=True)
