@@ -23,7 +23,7 @@ EXPORTS = [
     "agd_batch_create", "agd_batch_destroy", "agd_build_edges", "agd_forward", "agd_sample",
     "agd_extend_bond_order", "agd_op_cfconv_aggregate", "agd_op_eq_transform", "agd_debug_fetch",
     "agd_launch_count", "agd_profile_forward", "agd_forward_edges",
-    "agd_set_mode", "agd_get_mode", "agd_set_option", "agd_range_flag", "agd_f16_lo_shift",
+    "agd_set_mode", "agd_get_mode", "agd_set_option", "agd_range_flag", "agd_f16_lo_shift", "agd_debug_timing",
 ]
 
 
@@ -116,6 +116,7 @@ def load() -> C.CDLL:
     lib.agd_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     lib.agd_range_flag.argtypes = [vp, C.POINTER(i32)]
     lib.agd_f16_lo_shift.restype = C.c_int
+    lib.agd_debug_timing.argtypes = [vp, vp]
     if lib.agd_abi_version() != 1:
         raise ImportError("libagdiff_b200.so ABI version mismatch")
     _lib = lib

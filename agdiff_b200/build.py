@@ -38,6 +38,7 @@ def _digest() -> str:
                 h.update(name.encode())
                 h.update(open(p, "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("AGD_BUILD_DEFS", "").encode())
     return h.hexdigest()
 
 
@@ -50,6 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
     extra = ["-Xptxas", "-v"] if verbose else []
+    extra += os.environ.get("AGD_BUILD_DEFS", "").split()     # e.g. AGD_BUILD_DEFS=-DAGD_F16_TIMING (diagnostic builds)
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))

@@ -53,6 +53,7 @@ struct agd_handle {
   int64_t launches = 0;
   int f16_fuse = 1;
   int f16_debug_filt = 0;
+  unsigned long long* f16_timing = nullptr;
   int use_tc = 2;   // AGD_TC_FILTERS / agd_set_mode: 0 FFMA, 1 tcgen05 3xTF32, 2 tcgen05 + 3xFP16 filter kernels
 };
 
@@ -134,6 +135,7 @@ static LaunchCtx make_ctx(agd_handle* h) {
   c.use_tc = h->use_tc;
   c.f16_fuse = h->f16_fuse;
   c.f16_debug_filt = h->f16_debug_filt;
+  c.f16_timing = h->f16_timing;
   c.cutoff = h->cfg.cutoff;
   c.smooth = h->cfg.smooth_conv;
   c.num_convs = h->cfg.num_convs;
@@ -174,6 +176,7 @@ static void run_local_branch(const LaunchCtx& c, const BatchDev& b, const ModelW
 static void run_global_branch(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos, bool build = true) {
   if (build) launch_build_edges(c, b, pos);
   if (c.use_tc) launch_encoder_global_tc(c, b, w); else launch_encoder_global(c, b, w);
+  if (c.use_tc == 2) launch_edge_weights_f16(c, b, w);
   if (c.use_tc) launch_schnet_node_tc(c, b, w, -1); else launch_schnet_node(c, b, w, -1);
   for (int k = 0; k < c.num_convs; ++k) {
     launch_filters(c, b, w, k);
@@ -303,6 +306,7 @@ static void carve(BatchDev& d, Carver& c) {
   d.ea_loc = c.take<float>(L * HID);
   d.g2 = c.take<float>(E * HID);
   d.g2h = c.take<uint4>(((E + TM - 1) / TM) * TM * (HID / 4));
+  d.cw_all = c.take<float>(E * 2 * MAX_BLOCKS);
   d.filt = c.take<float>(E * 192);
   d.h = c.take<float>(N * HID);
   d.xcat = c.take<float>(N * 192);
@@ -484,34 +488,70 @@ int agd_sample(agd_handle* h, agd_batch* b, float* pos, const agd_sample_params*
   for (int s = 0; s < p->n_steps; ++s) (p->use_global[s] ? any_global : any_local) = true;
 
   if (p->use_cuda_graph) {
-    // two instantiations per step type, launched alternately: back-to-back launches of the SAME exec cannot overlap their
-    // launch set-up with the previous replay (measured: 0.5 ms per 46-node global step), two execs ping-pong
-    cudaGraphExec_t exec[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    int64_t per_graph_launches[2] = {0, 0};
+    // Per step type (local-only / local+global) two graphs are captured: one step, and a chunk of CHUNK consecutive steps
+    // (the device-side step counter makes a multi-step graph valid for any run of equal-type steps).  A graph launch costs
+    // ~0.5 ms of front-end time per ~50-node replay that does NOT overlap with the previous replay (measured: replaying a
+    // one-step graph is 10 % slower than plain launches), so it is amortised over CHUNK steps; two instantiations of the
+    // chunk graph are launched alternately.
+    int chunk = 8;
+    if (const char* e = std::getenv("AGD_GRAPH_CHUNK")) chunk = std::atoi(e) > 0 ? std::atoi(e) : 1;
+    cudaGraphExec_t exec_one[2] = {nullptr, nullptr};
+    cudaGraphExec_t exec_chunk[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int64_t per_step_launches[2] = {0, 0};
+    auto destroy_all = [&]() {
+      for (int g = 0; g < 2; ++g) {
+        if (exec_one[g]) cudaGraphExecDestroy(exec_one[g]);
+        for (int k = 0; k < 2; ++k)
+          if (exec_chunk[g][k]) cudaGraphExecDestroy(exec_chunk[g][k]);
+      }
+    };
+    // longest run of equal-type steps decides whether a chunk graph is worth building
+    int longest[2] = {0, 0};
+    for (int s = 0; s < p->n_steps;) {
+      int e = s;
+      while (e < p->n_steps && (p->use_global[e] != 0) == (p->use_global[s] != 0)) ++e;
+      const int g = p->use_global[s] ? 1 : 0;
+      if (e - s > longest[g]) longest[g] = e - s;
+      s = e;
+    }
     for (int g = 0; g < 2; ++g) {
       if (!(g ? any_global : any_local)) continue;
-      cudaGraph_t graph = nullptr;
-      const int64_t before = h->launches;
-      CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-      one_step(g == 1);
-      cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
-      per_graph_launches[g] = h->launches - before;
-      h->launches = before;
-      if (e != cudaSuccess) return fail(AGD_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
-      for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaGraphInstantiate(&exec[g][k], graph, 0);
-      cudaGraphDestroy(graph);
-      if (e != cudaSuccess) return fail(AGD_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+      for (int kind = 0; kind < 2; ++kind) {   // 0: one step, 1: chunk
+        if (kind == 1 && (chunk < 2 || longest[g] < chunk)) continue;
+        cudaGraph_t graph = nullptr;
+        const int64_t before = h->launches;
+        CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        for (int r = 0; r < (kind ? chunk : 1); ++r) one_step(g == 1);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        if (kind == 0) per_step_launches[g] = h->launches - before;
+        h->launches = before;
+        if (e != cudaSuccess) { destroy_all(); return fail(AGD_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e)); }
+        if (kind == 0) e = cudaGraphInstantiate(&exec_one[g], graph, 0);
+        else
+          for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaGraphInstantiate(&exec_chunk[g][k], graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { destroy_all(); return fail(AGD_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e)); }
+      }
     }
     cudaError_t e = cudaSuccess;
-    for (int s = 0; s < p->n_steps && e == cudaSuccess; ++s) {
+    int flip = 0;
+    for (int s = 0; s < p->n_steps && e == cudaSuccess;) {
       const int g = p->use_global[s] ? 1 : 0;
-      e = cudaGraphLaunch(exec[g][s & 1], h->stream);
-      h->launches += per_graph_launches[g];
+      int run = 1;
+      while (run < chunk && s + run < p->n_steps && (p->use_global[s + run] != 0) == (g == 1)) ++run;
+      if (run == chunk && exec_chunk[g][0]) {
+        e = cudaGraphLaunch(exec_chunk[g][flip], h->stream);
+        flip ^= 1;
+        h->launches += per_step_launches[g] * chunk;
+        s += chunk;
+      } else {
+        e = cudaGraphLaunch(exec_one[g], h->stream);
+        h->launches += per_step_launches[g];
+        s += 1;
+      }
     }
     cudaError_t e2 = cudaStreamSynchronize(h->stream);
-    for (int g = 0; g < 2; ++g)
-      for (int k = 0; k < 2; ++k)
-        if (exec[g][k]) cudaGraphExecDestroy(exec[g][k]);
+    destroy_all();
     if (e != cudaSuccess) return fail(AGD_ERR_CUDA, std::string("graph launch: ") + cudaGetErrorString(e));
     if (e2 != cudaSuccess) return fail(AGD_ERR_CUDA, std::string("sampling loop: ") + cudaGetErrorString(e2));
   } else {
@@ -559,6 +599,7 @@ int agd_op_cfconv_aggregate(const float* x, const float* W, const int32_t* src, 
   c.use_tc = 0;
   c.f16_fuse = 0;
   c.f16_debug_filt = 0;
+  c.f16_timing = nullptr;
   launch_aggregate(c, x, W, src, in_ptr, n_nodes, F, out);
   CUDA_TRY(cudaGetLastError());
   return AGD_OK;
@@ -609,10 +650,23 @@ int agd_set_option(agd_handle* h, const char* name, int value) {
   if (!h || !name) return fail(AGD_ERR_INVALID, "null argument");
   if (std::strcmp(name, "f16_fuse") == 0) h->f16_fuse = value ? 1 : 0;
   else if (std::strcmp(name, "f16_debug_filt") == 0) h->f16_debug_filt = value ? 1 : 0;
+  else if (std::strcmp(name, "f16_timing") == 0) {   // diagnostics: 1 = allocate + zero the phase counters, 0 = off
+    if (value && !h->f16_timing) {
+      if (cudaMalloc(&h->f16_timing, 64 * sizeof(unsigned long long)) != cudaSuccess) return fail(AGD_ERR_CUDA, "cudaMalloc");
+    }
+    if (value) cudaMemset(h->f16_timing, 0, 64 * sizeof(unsigned long long));
+    else if (h->f16_timing) { cudaFree(h->f16_timing); h->f16_timing = nullptr; }
+  }
   else return fail(AGD_ERR_INVALID, std::string("unknown option ") + name);
   return AGD_OK;
 }
 int agd_f16_lo_shift(void) { return f16_lo_shift(); }
+int agd_debug_timing(agd_handle* h, uint64_t* out64) {
+  if (!h || !out64 || !h->f16_timing) return fail(AGD_ERR_INVALID, "timing is off (agd_set_option f16_timing 1)");
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(out64, h->f16_timing, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return AGD_OK;
+}
 int agd_range_flag(agd_batch* b, int32_t* flag_out) {
   if (!b || !flag_out) return fail(AGD_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(b->h->cfg.device));

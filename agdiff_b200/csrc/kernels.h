@@ -87,6 +87,7 @@ struct BatchDev {
   // activations
   float* g2;                     // [cap][128]  encoder hidden state feeding filters and the pair MLP
   uint4* g2h;                    // [ceil(cap/128)*128][128 words] fp16-split copy of g2 (AGD_MODE_F16; layout: g2h_index in tc_common.cuh)
+  float* cw_all;                 // [2 * num_convs][cap] envelope * distance weight per CFConv layer (AGD_MODE_F16)
   float* filt;                   // [cap][192]  CFConv filters of the current block (conv1 | conv2)
   float *h, *xcat, *agg;         // [N][128], [N][192], [N][192]
   float *gx0, *gx1;              // [N][128] GIN ping-pong
@@ -117,6 +118,7 @@ struct LaunchCtx {
   Prof* prof;
   int use_tc;      // 0: fp32 FFMA tile kernels, 1: tcgen05 3xTF32 everywhere, 2: tcgen05 with 3xFP16 two-slot filter kernels
   int f16_debug_filt;   // fused kernels also write the filter tensor
+  unsigned long long* f16_timing;   // diagnostics: per-phase cycle counters of the f16 filter kernels (device, 64 values) or nullptr
   int f16_fuse;    // use_tc == 2: CFConv aggregation fused into the filter kernels (no filt tensor, no aggregate kernel)
   float cutoff;
   int smooth;
@@ -137,6 +139,7 @@ void launch_pair_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w, c
 // schnet.cu
 void launch_filters(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);
 void launch_filters_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);   // tc_filter.cu
+void launch_edge_weights_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& w);   // tc_filter16.cu, once per evaluation
 void launch_filters_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);  // tc_filter16.cu
 int f16_lo_shift();   // S of the fp16 lo' = (x - hi) * 2^S split (0: unscaled), pack.py must build the weight images with it
 int f16_fuse_default();    // AGD_F16_FUSE (default 1): launch_filters_f16 also performs the CFConv aggregation into agg

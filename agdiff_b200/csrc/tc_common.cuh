@@ -193,9 +193,13 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 // (low half = first value), hi = rn_f16(x), lo' = rn_f16((x - hi) * lo_scale); amax tracks max|x| for the range check.
 constexpr int F16_LO_SHIFT = 11;        // S: lo' = (x - hi) * 2^S (pack.umma_image_f16 builds the weight images with it)
 constexpr float F16_RANGE = 65000.f;
-__device__ __forceinline__ void split2_f16(float x0, float x1, float lo_scale, uint32_t& hi, uint32_t& lo, float& amax) {
-  amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
+__device__ __forceinline__ bool f16_out_of_range(__half2 amax) {
+  const float2 f = __half22float2(amax);
+  return fmaxf(f.x, f.y) > F16_RANGE;
+}
+__device__ __forceinline__ void split2_f16(float x0, float x1, float lo_scale, uint32_t& hi, uint32_t& lo, __half2& amax) {
   const __half2 h = __floats2half2_rn(x0, x1);
+  amax = __hmax2(amax, __habs2(h));            // inf when |x| is beyond the fp16 range; NaN operands are ignored
   const float2 hf = __half22float2(h);
   const __half2 l = __floats2half2_rn((x0 - hf.x) * lo_scale, (x1 - hf.y) * lo_scale);
   hi = *reinterpret_cast<const uint32_t*>(&h);

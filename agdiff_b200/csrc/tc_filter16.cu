@@ -62,6 +62,13 @@ __device__ __forceinline__ void mma_f16_ts_scaled(uint32_t d_tmem, uint32_t a_tm
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// streaming 16-byte load that does not allocate in L1 (the g2h tile stream must not evict the x rows the aggregation gathers)
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
   asm volatile(
@@ -86,21 +93,20 @@ constexpr int LDS_W = 68;               // padded row stride (floats) of the 64-
 struct TcF16Args {
   const uint32_t* W1img;   // [hi | lo'] fp16 images of F1 (K=128): each (128/64) x F rows x 128 B
   const uint32_t* W2img;   // ... of F2 (K=F)
-  const float *f1b, *f2b, *dw, *beta_ptr;
+  const float *f1b, *f2b, *beta_ptr;
+  const float* cw;         // [E] envelope * distance weight of this conv (edge_weight_kernel)
   const float* wsc;        // [0] = 1/scale(F1), [1] = 1/scale(F2)
   const int* n_rows_dev;
   const uint4* g2h;        // pre-split encoder state (tc_common.cuh: g2h_index)
-  const float* e_len;
   float* filt;             // [E][192]  (!FUSE)
   int col0;                // 0 (conv1) or 128 (conv2): column offset in filt / xcat / agg
-  float cutoff;
-  int smooth;
   int scaled;              // 1: lo' scaled by 2^S + scale-input-d, 0: unscaled lo (A/B switch AGD_F16_LOSHIFT=0)
   int* range_flag;
   int debug_filt;          // FUSE: also write the filter tensor (tests / diagnostics)
+  unsigned long long* timing;   // diagnostics: [group][observer 0/1][8 phases] accumulated cycles (nullptr: off)
   // fused aggregation (FUSE): agg[dst][col0 + n] = sum over the destination's edges, in CSC order, of x[src][col0 + n] * W_e[n]
   const float* xcat;       // [N][192]
-  float* agg;              // [N][192], zeroed before the launch
+  float* agg;              // [N][192]; rows of atoms without in-edges are not written (tc_node_kernel treats them as zero)
   const int *e_src, *e_dst, *in_ptr;
 };
 
@@ -108,9 +114,46 @@ template <int F, bool FUSE>
 struct TcF16Smem {
   static constexpr uint32_t W1_HALF = 128u * F * 2u, W2_HALF = static_cast<uint32_t>(F) * F * 2u;
   static constexpr size_t fuse_bytes = FUSE ? (2 * TM * LDS_W + 2 * 128) * sizeof(float) + 6 * TM * sizeof(int) : 0;
-  static constexpr size_t bytes = 1024 + 2 * W1_HALF + 2 * W2_HALF + (128 + 128 + 128 + 256) * sizeof(float) + fuse_bytes +
+  static constexpr size_t bytes = 1024 + 2 * W1_HALF + 2 * W2_HALF + (128 + 128) * sizeof(float) + fuse_bytes +
                                   16 * sizeof(uint64_t) + 64;
 };
+
+// softplus(y) - ln2 with the argument already in log2 units (y2 = y * log2 e): ln2 * (log2(1 + 2^y2) - 1); the
+// linear branch of F.softplus' threshold (y > 20) keeps the MUFU chain from overflowing
+__device__ __forceinline__ float ssp_log2(float y2) {
+  float e, sp;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y2));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(sp) : "f"(1.0f + e));
+  return fmaf((y2 > 28.853900817779268f) ? y2 : sp, LN2F, -LN2F);
+}
+
+// CFConv edge weight lw(d) * C(d) (schnet.py:90-100,140-147) with the distance MLP staged in shared memory [w1 | b1 | w2 | b2],
+// read as float4 (same arithmetic, in the same order, as cfconv_edge_weight_smem)
+__device__ __forceinline__ float edge_weight_vec(float d, const float* dw, float cutoff, int smooth) {
+  float z = dw[96];
+  const float4* w1 = reinterpret_cast<const float4*>(dw);
+  const float4* b1 = reinterpret_cast<const float4*>(dw + 32);
+  const float4* w2 = reinterpret_cast<const float4*>(dw + 64);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 a4 = w1[q], b4 = b1[q], c4 = w2[q];
+    z = fmaf(c4.x, relu_(fmaf(a4.x, d, b4.x)), z);
+    z = fmaf(c4.y, relu_(fmaf(a4.y, d, b4.y)), z);
+    z = fmaf(c4.z, relu_(fmaf(a4.z, d, b4.z)), z);
+    z = fmaf(c4.w, relu_(fmaf(a4.w, d, b4.w)), z);
+  }
+  const float lw = sigmoidf_(z);
+  float C;
+  if (smooth) {
+    C = 0.5f * (cosf(d * 3.14159265358979323846f / cutoff) + 1.0f);
+    C = (d <= cutoff) ? C : 0.f;
+  } else {
+    const float t = d - cutoff;
+    C = expf(-(t * t) / (2.0f * cutoff * cutoff));
+  }
+  C = (d <= cutoff && d >= 0.f) ? C : 0.f;
+  return lw * C;
+}
 
 // the 3 x K/16 MMAs of one layer for one slot, issued by ONE thread: cross terms first, then the main chain
 template <int K, int N>
@@ -151,22 +194,46 @@ __device__ __forceinline__ void aggregate_half(const TcF16Args& a, const RunCtx&
                                                const float* carry_other, uint64_t* full_mine, uint64_t* empty_mine,
                                                uint64_t* full_other, uint64_t* empty_other, uint32_t prod_cnt, uint32_t cons_cnt,
                                                int gwarp, int lane) {
-  constexpr int PASSES = F / 64;
   const int colg = a.col0 + pass * 64 + 2 * lane;   // this lane's two columns in xcat / agg
+  // descending, so that run 0 - the only one that may have to wait for the other group's carry - comes last
 #pragma unroll 1
-  for (int k = gwarp; k < rc.n_runs; k += F16_GWARPS) {
+  for (int k = gwarp + ((rc.n_runs - 1 - gwarp) & ~(F16_GWARPS - 1)); k >= 0 && k < rc.n_runs; k -= F16_GWARPS) {
     const int s = s_runs[k];
     const int e = (k + 1 < rc.n_runs) ? s_runs[k + 1] : rc.n_valid;
     float2 acc = make_float2(0.f, 0.f);
     if (k == 0 && rc.carry_in) {
-      if (pass == 0) tc::mbar_wait(full_other, cons_cnt & 1u);
+      tc::mbar_wait(full_other, cons_cnt & 1u);
       acc = *reinterpret_cast<const float2*>(carry_other + pass * 64 + 2 * lane);
-      if (pass == PASSES - 1) {
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(empty_other);
-      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(empty_other);
     }
     int row = s;
+    for (; row + 16 <= e; row += 16) {
+      float2 xv[16], wv[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        xv[u] = __ldg(reinterpret_cast<const float2*>(a.xcat + (size_t)s_src[row + u] * 192 + colg));
+        wv[u] = *reinterpret_cast<const float2*>(s_W + (row + u) * LDS_W + 2 * lane);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        acc.x = fmaf(xv[u].x, wv[u].x, acc.x);
+        acc.y = fmaf(xv[u].y, wv[u].y, acc.y);
+      }
+    }
+    for (; row + 8 <= e; row += 8) {
+      float2 xv[8], wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        xv[u] = __ldg(reinterpret_cast<const float2*>(a.xcat + (size_t)s_src[row + u] * 192 + colg));
+        wv[u] = *reinterpret_cast<const float2*>(s_W + (row + u) * LDS_W + 2 * lane);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc.x = fmaf(xv[u].x, wv[u].x, acc.x);
+        acc.y = fmaf(xv[u].y, wv[u].y, acc.y);
+      }
+    }
     for (; row + 4 <= e; row += 4) {
       float2 xv[4], wv[4];
 #pragma unroll
@@ -187,12 +254,10 @@ __device__ __forceinline__ void aggregate_half(const TcF16Args& a, const RunCtx&
       acc.y = fmaf(xv.y, wv.y, acc.y);
     }
     if (k == rc.n_runs - 1 && rc.carry_out) {
-      if (pass == 0) tc::mbar_wait(empty_mine, (prod_cnt & 1u) ^ 1u);   // the previous carry of this group was consumed
+      tc::mbar_wait(empty_mine, (prod_cnt & 1u) ^ 1u);   // the previous carry of this group (same pass) was consumed
       *reinterpret_cast<float2*>(carry_mine + pass * 64 + 2 * lane) = acc;
-      if (pass == PASSES - 1) {
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(full_mine);
-      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(full_mine);
     } else {
       *reinterpret_cast<float2*>(a.agg + (size_t)s_dst[s] * 192 + colg) = acc;
     }
@@ -211,14 +276,12 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
   uint8_t* w2 = base + 2 * W1_HALF;
   float* s_b1 = reinterpret_cast<float*>(w2 + 2 * W2_HALF);
   float* s_b2 = s_b1 + 128;
-  float* s_dw = s_b2 + 128;
-  float* s_cw = s_dw + 128;                                        // [2][128] envelope weight of each slot's rows
-  float* s_Wt = s_cw + 256;                                        // FUSE: [2][128][LDS_W] filter half-tiles
+  float* s_Wt = s_b2 + 128;                                        // FUSE: [2][128][LDS_W] filter half-tiles
   float* s_carry = s_Wt + (FUSE ? 2 * TM * LDS_W : 0);             // FUSE: [2][128] partial sums of runs cut by a tile boundary
   int* s_srcdst = reinterpret_cast<int*>(s_carry + (FUSE ? 256 : 0));   // FUSE: [2][3][128] src / dst / run starts of each slot's rows
-  // [0] weights landed, [1+g] operand ready, [3+g] accumulator ready, [5+g] carry full, [7+g] carry empty
+  // [0] weights landed, [1+g] operand ready, [3+g] accumulator ready, [5+2g+pass] carry full, [9+2g+pass] carry empty
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_srcdst + (FUSE ? 6 * TM : 0));
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_rows = *a.n_rows_dev;
@@ -242,14 +305,13 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], F16_GROUP);
     mbar_init(&bars[2], F16_GROUP);
-    for (int i = 3; i < 9; ++i) mbar_init(&bars[i], 1);
+    for (int i = 3; i < 13; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
   }
-  if (tid < F) {
-    s_b1[tid] = __ldg(a.f1b + tid);
+  if (tid < F) {   // layer-1 bias pre-multiplied by beta * log2(e): the epilogue's first FFMA yields the exponent argument directly
+    s_b1[tid] = __ldg(a.f1b + tid) * (__ldg(a.beta_ptr) * 1.4426950408889634f);
     s_b2[tid] = __ldg(a.f2b + tid);
   }
-  if (tid >= 128 && tid < 256) s_dw[tid - 128] = __ldg(a.dw + tid - 128);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -270,15 +332,13 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
     const uint32_t trow = slot + (static_cast<uint32_t>(quad * 32) << 16);
     uint64_t* a_ready = &bars[1 + g];
     uint64_t* d_ready = &bars[3 + g];
-    float* cwbuf = s_cw + g * 128;
     float* s_W = s_Wt + g * TM * LDS_W;
     int* s_src = s_srcdst + g * 3 * TM;
     int* s_dst = s_src + TM;
     int* s_runs = s_dst + TM;
-    const float beta = __ldg(a.beta_ptr);
-    const float inv1 = __ldg(a.wsc + 0), inv2 = __ldg(a.wsc + 1);
+    const float inv1 = __ldg(a.wsc + 0) * (__ldg(a.beta_ptr) * 1.4426950408889634f), inv2 = __ldg(a.wsc + 1);
     const float lo_scale = a.scaled ? static_cast<float>(1 << F16_LO_SHIFT) : 1.0f;
-    float amax = 0.f;
+    __half2 amax = __floats2half2_rn(0.f, 0.f);
     uint32_t dph = 0, aph = 0, prod_cnt = 0, cons_cnt = 0;
     const bool issuer = (tid & (F16_GROUP - 1)) == 0;
     const bool scaled = a.scaled != 0;
@@ -286,36 +346,27 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
 
     // this thread's slice of the pre-split g2 row: 32 hi words + 32 lo' words (K = 64*half .. 64*half+63), one tile ahead
     uint4 pre[16];
-    float pre_len = -1.f;
+    float pre_len = 0.f;   // the row's edge weight cw, travels with the operand prefetch
     auto prefetch = [&](int j) {
       const int64_t row0 = cta_begin + static_cast<int64_t>(j) * TM;
       const int64_t r = row0 + my_row;
       if (j < cta_tiles && r < cta_end) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          pre[q] = __ldg(a.g2h + g2h_index(r, 8 * half + q));
-          pre[8 + q] = __ldg(a.g2h + g2h_index(r, 16 + 8 * half + q));
+          pre[q] = ldg_stream(a.g2h + g2h_index(r, 8 * half + q));
+          pre[8 + q] = ldg_stream(a.g2h + g2h_index(r, 16 + 8 * half + q));
         }
-        pre_len = __ldg(a.e_len + r);
+        pre_len = __ldg(a.cw + r);
       } else {
 #pragma unroll
         for (int q = 0; q < 16; ++q) pre[q] = make_uint4(0u, 0u, 0u, 0u);
-        pre_len = -1.f;
+        pre_len = 0.f;
       }
     };
 
-    prefetch(g);
-    for (int j = g; j < cta_tiles; j += 2) {
-      const int64_t row0 = cta_begin + static_cast<int64_t>(j) * TM;
-      const int n_valid = (cta_end - row0 < TM) ? static_cast<int>(cta_end - row0) : TM;
-      const int64_t r = row0 + my_row;
-      const bool valid = my_row < n_valid;
-      // ---- stage A: the pre-split g2 rows go straight into the slot's operand columns
-      if (half == 1) cwbuf[my_row] = valid ? cfconv_edge_weight_smem(pre_len, s_dw, a.cutoff, a.smooth) : 0.f;
-      if (FUSE && half == 0) {
-        s_src[my_row] = valid ? __ldg(a.e_src + r) : 0;
-        s_dst[my_row] = valid ? __ldg(a.e_dst + r) : -1;
-      }
+    // prefetched operand rows -> the slot's operand columns.  Called once layer 2 of the previous tile has completed (the A
+    // columns are dead from then on), so the 64 prefetch registers are free again before the aggregation needs them.
+    auto stage_operand = [&]() {
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t hi[16], lo[16];
@@ -327,10 +378,42 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
         tmem_st16(trow + C16_AHI + half * 32 + c * 16, hi);
         tmem_st16(trow + C16_ALO + half * 32 + c * 16, lo);
       }
+    };
+
+    // phase timing (diagnostics only, compiled in with -DAGD_F16_TIMING: it costs ~20 registers): observers = first lane of
+    // the group's warp 0 and warp 7
+#ifdef AGD_F16_TIMING
+    const bool obs = a.timing != nullptr && lane == 0 && (gwarp == 0 || gwarp == 7);
+    long long t_prev = obs ? clock64() : 0;
+    unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    auto tick = [&](int phase) {
+      if (obs) {
+        const long long t = clock64();
+        t_acc[phase] += static_cast<unsigned long long>(t - t_prev);
+        t_prev = t;
+      }
+    };
+#else
+    auto tick = [](int) {};
+#endif
+
+    prefetch(g);
+    stage_operand();
+    float len_cur = pre_len;
+    for (int j = g; j < cta_tiles; j += 2) {
+      const int64_t row0 = cta_begin + static_cast<int64_t>(j) * TM;
+      const int n_valid = (cta_end - row0 < TM) ? static_cast<int>(cta_end - row0) : TM;
+      const int64_t r = row0 + my_row;
+      const bool valid = my_row < n_valid;
+      // ---- the operand rows are already in the slot (stage_operand); endpoints of the rows -> smem
+      if (FUSE && half == 0) {
+        s_src[my_row] = valid ? __ldg(a.e_src + r) : 0;
+        s_dst[my_row] = valid ? __ldg(a.e_dst + r) : -1;
+      }
       wait_st();
       fence_before_sync();
       group_sync(1 + g, F16_GROUP);
-      const float cw = cwbuf[my_row];
+      tick(0);
       mbar_arrive(a_ready);
       if (issuer) {
         mbar_wait(a_ready, aph);
@@ -339,6 +422,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
         issue_3xf16<HID, F>(slot, smem_u32(w1), W1_HALF, scaled);
         mma_commit(d_ready);
       }
+      const float cw = valid ? len_cur : 0.f;   // envelope * distance weight of this thread's row (edge_weight_kernel)
       // run structure of this tile (FUSE; every warp computes the same masks while layer 1 runs)
       RunCtx rc;
       if (FUSE) {
@@ -352,7 +436,15 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
           const int dp = (row > 0) ? s_dst[row - 1] : -3;
           const bool start = row < n_valid && (row == 0 || d != dp);
           const uint32_t m = __ballot_sync(0xffffffffu, start);
-          if (gwarp == 0 && start) s_runs[below + __popc(m & ((1u << lane) - 1u))] = row;   // published by the next group_sync
+          const int start_rank = below + __popc(m & ((1u << lane) - 1u));
+          if (gwarp == 0 && start) s_runs[start_rank] = row;   // published by the next group_sync
+          // the x rows this warp will gather (runs gwarp, gwarp + 8, ...) -> L1 while the tensor core runs layer 1
+          const int run = below + __popc(m & (0xffffffffu >> (31 - lane))) - 1;
+          if (row < n_valid && (run & (F16_GWARPS - 1)) == gwarp) {
+            const float* px = a.xcat + (size_t)s_src[row] * 192 + a.col0;
+#pragma unroll
+            for (int l = 0; l < F / 32; ++l) prefetch_l1(px + 32 * l);
+          }
           below += __popc(m);
         }
         rc.n_runs = below;
@@ -363,6 +455,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
       mbar_wait(d_ready, dph);
       dph ^= 1u;
       fence_after_sync();
+      tick(1);
 #pragma unroll
       for (int c = 0; c < HC / 32; ++c) {
         const int n0 = half * HC + c * 32;
@@ -372,8 +465,8 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-          const float t0 = ssp_fast(fmaf(__uint_as_float(v[2 * q]), inv1, s_b1[n0 + 2 * q]), beta);
-          const float t1 = ssp_fast(fmaf(__uint_as_float(v[2 * q + 1]), inv1, s_b1[n0 + 2 * q + 1]), beta);
+          const float t0 = ssp_log2(fmaf(__uint_as_float(v[2 * q]), inv1, s_b1[n0 + 2 * q]));
+          const float t1 = ssp_log2(fmaf(__uint_as_float(v[2 * q + 1]), inv1, s_b1[n0 + 2 * q + 1]));
           split2_f16(t0, t1, lo_scale, hi[q], lo[q], amax);
         }
         tmem_st16(trow + C16_AHI + (n0 >> 1), hi);
@@ -381,6 +474,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
       }
       wait_st();
       fence_before_sync();
+      tick(2);
       mbar_arrive(a_ready);
       if (issuer) {
         mbar_wait(a_ready, aph);
@@ -394,29 +488,45 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
       mbar_wait(d_ready, dph);
       dph ^= 1u;
       fence_after_sync();
+      tick(3);
+      if (!FUSE) {
+        stage_operand();   // next tile's operand rows (prefetched during layer 2) -> TMEM
+        len_cur = pre_len;
+      }
       if (FUSE) {
         // two column halves per thread are staged as 64-column half-tiles: pass p holds filter columns [64p, 64p+64)
 #pragma unroll 1
         for (int pass = 0; pass < F / 64; ++pass) {
           const int n0 = pass * 64 + half * 32;
-          uint32_t v[32];
-          tmem_ld32(trow + C16_D + n0, v);
-          wait_ld();
           float4* dstW = reinterpret_cast<float4*>(s_W + my_row * LDS_W + half * 32);
+          {
+            uint32_t v[32];
+            tmem_ld32(trow + C16_D + n0, v);
+            wait_ld();
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 o;
-            o.x = fmaf(__uint_as_float(v[q * 4 + 0]), inv2, s_b2[n0 + q * 4 + 0]) * cw;
-            o.y = fmaf(__uint_as_float(v[q * 4 + 1]), inv2, s_b2[n0 + q * 4 + 1]) * cw;
-            o.z = fmaf(__uint_as_float(v[q * 4 + 2]), inv2, s_b2[n0 + q * 4 + 2]) * cw;
-            o.w = fmaf(__uint_as_float(v[q * 4 + 3]), inv2, s_b2[n0 + q * 4 + 3]) * cw;
-            dstW[q] = o;
-            if (a.debug_filt && valid) *reinterpret_cast<float4*>(a.filt + r * 192 + a.col0 + n0 + q * 4) = o;
+            for (int q = 0; q < 8; ++q) {
+              const int n = n0 + q * 4;
+              float4 o;
+              o.x = fmaf(__uint_as_float(v[q * 4 + 0]), inv2, s_b2[n + 0]) * cw;
+              o.y = fmaf(__uint_as_float(v[q * 4 + 1]), inv2, s_b2[n + 1]) * cw;
+              o.z = fmaf(__uint_as_float(v[q * 4 + 2]), inv2, s_b2[n + 2]) * cw;
+              o.w = fmaf(__uint_as_float(v[q * 4 + 3]), inv2, s_b2[n + 3]) * cw;
+              dstW[q] = o;
+              if (a.debug_filt && valid) *reinterpret_cast<float4*>(a.filt + r * 192 + a.col0 + n) = o;
+            }
+          }
+          if (pass == 0) {   // next tile's operand rows (prefetched during layer 2) -> TMEM; frees the 64 prefetch registers
+            stage_operand();
+            len_cur = pre_len;
           }
           group_sync(1 + g, F16_GROUP);    // half-tile complete
-          aggregate_half<F>(a, rc, s_W, s_src, s_dst, s_runs, pass, s_carry + g * 128, s_carry + (1 - g) * 128, &bars[5 + g],
-                            &bars[7 + g], &bars[5 + (1 - g)], &bars[7 + (1 - g)], prod_cnt, cons_cnt, gwarp, lane);
+          tick(4);
+          aggregate_half<F>(a, rc, s_W, s_src, s_dst, s_runs, pass, s_carry + g * 128, s_carry + (1 - g) * 128,
+                            &bars[5 + 2 * g + pass], &bars[9 + 2 * g + pass], &bars[5 + 2 * (1 - g) + pass],
+                            &bars[9 + 2 * (1 - g) + pass], prod_cnt, cons_cnt, gwarp, lane);
+          tick(5);
           group_sync(1 + g, F16_GROUP);    // half-tile consumed (s_W, and after the last pass s_src / s_dst / s_runs, may be rewritten)
+          tick(6);
         }
         if (rc.carry_out) ++prod_cnt;      // every warp of the group counts the same hand-offs
         if (rc.carry_in) ++cons_cnt;
@@ -444,11 +554,58 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
       // the next tile's operand stores target the A columns (dead since layer 2 completed); D is only overwritten after this
       // thread's next arrive on a_ready, which follows the wait::ld above in program order
     }
-    if (amax > F16_RANGE) atomicOr(a.range_flag, 1);
+    if (f16_out_of_range(amax)) atomicOr(a.range_flag, 1);
+#ifdef AGD_F16_TIMING
+    if (obs)
+      for (int i = 0; i < 8; ++i) atomicAdd(a.timing + (g * 2 + (gwarp == 7 ? 1 : 0)) * 8 + i, t_acc[i]);
+#endif
   }
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---- envelope * learnable distance weight of every edge for all CFConv layers of the step (schnet.py:90-100,140-147), once
+// per network evaluation instead of inside each of the 12 filter launches (where its ~350 dependent instructions per row
+// sat on the tile pipeline's critical path).  cw[net][e], net = 2 * block + conv.
+struct EdgeWArgs {
+  const float* dw[2 * MAX_BLOCKS];
+  int n_nets;
+  const int* n_rows_dev;
+  const float* e_len;
+  float* cw;
+  int64_t stride;
+  float cutoff;
+  int smooth;
+};
+__global__ void __launch_bounds__(256) edge_weight_kernel(const EdgeWArgs a) {
+  __shared__ __align__(16) float s_dw[2 * MAX_BLOCKS][128];
+  for (int i = threadIdx.x; i < a.n_nets * 128; i += blockDim.x) s_dw[i >> 7][i & 127] = __ldg(a.dw[i >> 7] + (i & 127));
+  __syncthreads();
+  const int n = *a.n_rows_dev;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float d = __ldg(a.e_len + e);
+    for (int k = 0; k < a.n_nets; ++k) a.cw[k * a.stride + e] = edge_weight_vec(d, s_dw[k], a.cutoff, a.smooth);
+  }
+}
+
+void launch_edge_weights_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& mw) {
+  EdgeWArgs a{};
+  a.n_nets = 2 * c.num_convs;
+  for (int k = 0; k < c.num_convs; ++k) {
+    a.dw[2 * k] = mw.blk[k].dw1;
+    a.dw[2 * k + 1] = mw.blk[k].dw2;
+  }
+  a.n_rows_dev = b.counters;
+  a.e_len = b.e_len;
+  a.cw = b.cw_all;
+  a.stride = b.cap > 0 ? b.cap : 1;
+  a.cutoff = c.cutoff;
+  a.smooth = c.smooth;
+  int64_t blocks = (b.cap + 255) / 256;
+  const int grid = (int)(blocks < 1 ? 1 : (blocks > 8 * c.num_sms ? 8 * c.num_sms : blocks));
+  edge_weight_kernel<<<grid, 256, 0, c.stream>>>(a);
+  note_launch(c, "schnet.edge_weights");
 }
 
 static int env_flag(const char* name, int dflt) {
@@ -470,27 +627,25 @@ void launch_filters_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& mw,
   TcF16Args a{};
   a.n_rows_dev = b.counters;
   a.g2h = b.g2h;
-  a.e_len = b.e_len;
   a.filt = b.filt;
-  a.cutoff = c.cutoff;
-  a.smooth = c.smooth;
   a.scaled = scaled;
   a.range_flag = b.counters + 4;
   a.debug_filt = c.f16_debug_filt;
+  a.timing = c.f16_timing;
   a.xcat = b.xcat;
   a.agg = b.agg;
   a.e_src = b.e_src;
   a.e_dst = b.e_dst;
   a.in_ptr = b.in_ptr;
-  if (fuse) cudaMemsetAsync(b.agg, 0, sizeof(float) * 192 * (size_t)b.n_atoms, c.stream);   // atoms without in-edges
+  // (atoms without in-edges: their agg rows stay unwritten, tc_node_kernel reads them as zero via in_ptr)
   int64_t pairs = (b.cap + 2 * TM - 1) / (2 * TM);
   const int grid = (int)(pairs < c.num_sms ? (pairs < 1 ? 1 : pairs) : c.num_sms);
   a.W1img = reinterpret_cast<const uint32_t*>(w.hF1a); a.W2img = reinterpret_cast<const uint32_t*>(w.hF2a);
-  a.f1b = w.f1ab; a.f2b = w.f2ab; a.dw = w.dw1; a.beta_ptr = w.sc + 0; a.wsc = w.hsc + 0; a.col0 = 0;
+  a.f1b = w.f1ab; a.f2b = w.f2ab; a.cw = b.cw_all + (size_t)(2 * blk) * (b.cap > 0 ? b.cap : 1); a.beta_ptr = w.sc + 0; a.wsc = w.hsc + 0; a.col0 = 0;
   if (fuse) launch_one<128, true>(a, grid, c.stream); else launch_one<128, false>(a, grid, c.stream);
   note_launch(c, fuse ? "schnet.cfconv128_f16" : "schnet.filter128_f16");
   a.W1img = reinterpret_cast<const uint32_t*>(w.hF1b); a.W2img = reinterpret_cast<const uint32_t*>(w.hF2b);
-  a.f1b = w.f1bb; a.f2b = w.f2bb; a.dw = w.dw2; a.beta_ptr = w.sc + 1; a.wsc = w.hsc + 2; a.col0 = 128;
+  a.f1b = w.f1bb; a.f2b = w.f2bb; a.cw = b.cw_all + (size_t)(2 * blk + 1) * (b.cap > 0 ? b.cap : 1); a.beta_ptr = w.sc + 1; a.wsc = w.hsc + 2; a.col0 = 128;
   if (fuse) launch_one<64, true>(a, grid, c.stream); else launch_one<64, false>(a, grid, c.stream);
   note_launch(c, fuse ? "schnet.cfconv64_f16" : "schnet.filter64_f16");
 }

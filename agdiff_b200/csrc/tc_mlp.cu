@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) tc_encoder_kernel(const TcEncA
       else if (more) cx.stream(a.tW1, IMG128);
     }
     // ---- g2 = gelu(D + T2[type])
-    float amax = 0.f;
+    __half2 amax = __floats2half2_rn(0.f, 0.f);
     const float* T2 = a.w.T2 + type * HID;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) tc_encoder_kernel(const TcEncA
         }
       }
     }
-    if (!LOCAL && amax > F16_RANGE) atomicOr(a.range_flag, 1);
+    if (!LOCAL && f16_out_of_range(amax)) atomicOr(a.range_flag, 1);
     if (LOCAL) {
       cx.layer_streamed(128, 128, false);               // combination_mlp.2
       cx.wait_mma();

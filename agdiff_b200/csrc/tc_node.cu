@@ -26,6 +26,7 @@ struct TcNodeArgs {
   int n_nodes;
   int first;
   const float* agg;   // [N][192]
+  const int* in_ptr;  // [N+1] in-edge segments: atoms without in-edges aggregate to zero (their agg rows are not written by the fused kernels)
   float* h;           // [N][128]
   float* xcat;        // [N][192]
 };
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_node_kernel(const TcNodeArg
       if (tid == 0 && has_next) cx.stream(a.nL1a_img, IMG_128x128);
     } else {
       if (tid == 0) cx.stream(a.w.tL2a, IMG_128x128);
+      const bool has_in = valid && __ldg(a.in_ptr + r + 1) > __ldg(a.in_ptr + r);
       // ---- 1. A = agg[:, :128]; conv1.lin2 (+BN) -> t1 = SSP
       {
         const float4* pa = reinterpret_cast<const float4*>(a.agg + (valid ? r : 0) * 192 + part * 32);
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_node_kernel(const TcNodeArg
           float t[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 v = valid ? __ldg(pa + c * 4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 v = has_in ? __ldg(pa + c * 4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
             t[q * 4] = v.x; t[q * 4 + 1] = v.y; t[q * 4 + 2] = v.z; t[q * 4 + 3] = v.w;
           }
           st_split16(cx.trow, part * 32 + c * 16, t);
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_node_kernel(const TcNodeArg
           float t[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 v = valid ? __ldg(pa + c * 4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 v = has_in ? __ldg(pa + c * 4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
             t[q * 4] = v.x; t[q * 4 + 1] = v.y; t[q * 4 + 2] = v.z; t[q * 4 + 3] = v.w;
           }
           st_split16(cx.trow, part * 32 + c * 16, t);
@@ -490,6 +492,7 @@ void launch_schnet_node_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& 
   a.atom_type = b.atom_type;
   a.emb = w.sch_emb;
   a.agg = b.agg;
+  a.in_ptr = b.in_ptr;
   a.h = b.h;
   a.xcat = b.xcat;
   a.first = (blk < 0) ? 1 : 0;

@@ -204,6 +204,9 @@ int agd_set_option(agd_handle* h, const char* name, int value);
 int agd_range_flag(agd_batch* b, int32_t* flag_out);
 /* S of the fp16 split lo' = (x - hi) * 2^S the library was built/configured with; the packer builds the images with it */
 int agd_f16_lo_shift(void);
+/* diagnostics: after agd_set_option(h, "f16_timing", 1), the accumulated clock64 cycles per pipeline phase of the fp16
+ * filter kernels: out64[(group*2 + observer)*8 + phase], summed over CTAs and launches */
+int agd_debug_timing(agd_handle* h, uint64_t* out64);
 
 #ifdef __cplusplus
 }
