@@ -19,6 +19,7 @@ void set_tc_attributes();
 void set_tc_mlp_attributes();
 void set_tc_node_attributes();
 void set_tc16_attributes();
+void set_tc_mlp16_attributes();
 }  // namespace agd
 
 using namespace agd;
@@ -52,6 +53,8 @@ struct agd_handle {
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   int64_t launches = 0;
   int f16_fuse = 1;
+  int f16_mlp = 1;
+  int f16_pair = 1;
   int f16_debug_filt = 0;
   unsigned long long* f16_timing = nullptr;
   int use_tc = 2;   // AGD_TC_FILTERS / agd_set_mode: 0 FFMA, 1 tcgen05 3xTF32, 2 tcgen05 + 3xFP16 filter kernels
@@ -80,6 +83,9 @@ static void build_slots(agd_handle* h) {
   add("tenc.W1", 2 * H * H, &w.tenc_W1); add("tenc.M2", 2 * H * H, &w.tenc_M2); add("tenc.C2", 2 * H * H, &w.tenc_C2);
   add("tpg.P1h", 2 * H * H, &w.tpg_P1h); add("tpg.P1e", 2 * H * H, &w.tpg_P1e); add("tpg.P2", 2 * 64 * H, &w.tpg_P2);
   add("tpl.P1h", 2 * H * H, &w.tpl_P1h); add("tpl.P1e", 2 * H * H, &w.tpl_P1e); add("tpl.P2", 2 * 64 * H, &w.tpl_P2);
+  add("henc.W1", H * H, &w.henc_W1); add("henc.M2", H * H, &w.henc_M2); add("henc.C2", H * H, &w.henc_C2); add("henc.sc", 4, &w.henc_sc);
+  add("hpg.P1h", H * H, &w.hpg_P1h); add("hpg.P1e", H * H, &w.hpg_P1e); add("hpg.P2", 64 * H, &w.hpg_P2); add("hpg.sc", 4, &w.hpg_sc);
+  add("hpl.P1h", H * H, &w.hpl_P1h); add("hpl.P1e", H * H, &w.hpl_P1e); add("hpl.P2", 64 * H, &w.hpl_P2); add("hpl.sc", 4, &w.hpl_sc);
   add("sch.emb", 100 * H, &w.sch_emb);
   for (int k = 0; k < h->cfg.num_convs; ++k) {
     BlkW& b = w.blk[k];
@@ -134,6 +140,8 @@ static LaunchCtx make_ctx(agd_handle* h) {
   c.prof = nullptr;
   c.use_tc = h->use_tc;
   c.f16_fuse = h->f16_fuse;
+  c.f16_mlp = (h->use_tc == 2) ? h->f16_mlp : 0;
+  c.f16_pair = (h->use_tc == 2) ? h->f16_pair : 0;
   c.f16_debug_filt = h->f16_debug_filt;
   c.f16_timing = h->f16_timing;
   c.cutoff = h->cfg.cutoff;
@@ -159,7 +167,9 @@ static int leave(agd_handle* h, void* user_stream) {
 
 // ------------------------------------------------------------------ launch sequences
 static void run_local_branch(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos, const float** h_out) {
-  if (c.use_tc) launch_encoder_local_tc(c, b, w, pos); else launch_encoder_local(c, b, w, pos);
+  if (c.f16_mlp) launch_encoder_local_f16(c, b, w, pos);
+  else if (c.use_tc) launch_encoder_local_tc(c, b, w, pos);
+  else launch_encoder_local(c, b, w, pos);
   launch_gin_embed(c, b, w);
   const float* x_in = b.gx0;
   float* x_out = b.gx1;
@@ -169,13 +179,17 @@ static void run_local_branch(const LaunchCtx& c, const BatchDev& b, const ModelW
     x_in = x_out;
     x_out = const_cast<float*>(t);
   }
-  if (c.use_tc) launch_pair_local_tc(c, b, w, x_in); else launch_pair_local(c, b, w, x_in);
+  if (c.f16_pair) launch_pair_local_f16(c, b, w, x_in);
+  else if (c.use_tc) launch_pair_local_tc(c, b, w, x_in);
+  else launch_pair_local(c, b, w, x_in);
   if (h_out) *h_out = x_in;
 }
 
 static void run_global_branch(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos, bool build = true) {
   if (build) launch_build_edges(c, b, pos);
-  if (c.use_tc) launch_encoder_global_tc(c, b, w); else launch_encoder_global(c, b, w);
+  if (c.f16_mlp) launch_encoder_global_f16(c, b, w);
+  else if (c.use_tc) launch_encoder_global_tc(c, b, w);
+  else launch_encoder_global(c, b, w);
   if (c.use_tc == 2) launch_edge_weights_f16(c, b, w);
   if (c.use_tc) launch_schnet_node_tc(c, b, w, -1); else launch_schnet_node(c, b, w, -1);
   for (int k = 0; k < c.num_convs; ++k) {
@@ -183,7 +197,9 @@ static void run_global_branch(const LaunchCtx& c, const BatchDev& b, const Model
     if (!((c.use_tc == 1 && filters_tc_fused()) || (c.use_tc == 2 && c.f16_fuse))) launch_aggregate(c, b.xcat, b.filt, b.e_src, b.in_ptr, b.n_atoms, 192, b.agg);
     if (c.use_tc) launch_schnet_node_tc(c, b, w, k); else launch_schnet_node(c, b, w, k);
   }
-  if (c.use_tc) launch_pair_global_tc(c, b, w); else launch_pair_global(c, b, w);
+  if (c.f16_pair) launch_pair_global_f16(c, b, w);
+  else if (c.use_tc) launch_pair_global_tc(c, b, w);
+  else launch_pair_global(c, b, w);
 }
 
 extern "C" {
@@ -217,7 +233,10 @@ int agd_create(const agd_config* cfg, agd_handle** out) {
   set_tc_mlp_attributes();
   set_tc_node_attributes();
   set_tc16_attributes();
+  set_tc_mlp16_attributes();
   h->f16_fuse = f16_fuse_default();
+  if (const char* e = std::getenv("AGD_F16_MLP")) h->f16_mlp = (e[0] != '0');
+  if (const char* e = std::getenv("AGD_F16_PAIR")) h->f16_pair = (e[0] != '0');
   if (const char* e = std::getenv("AGD_TC_FILTERS")) h->use_tc = (e[0] == '0') ? 0 : (e[0] == '1') ? 1 : 2;
   CUDA_TRY(cudaGetLastError());
   *out = h;
@@ -313,6 +332,7 @@ static void carve(BatchDev& d, Carver& c) {
   d.agg = c.take<float>(N * 192);
   d.gx0 = c.take<float>(N * HID);
   d.gx1 = c.take<float>(N * HID);
+  d.hmax = c.take<float>(N);
 }
 
 static int check_desc(const agd_batch_desc* d) {
@@ -598,6 +618,8 @@ int agd_op_cfconv_aggregate(const float* x, const float* W, const int32_t* src, 
   c.prof = nullptr;
   c.use_tc = 0;
   c.f16_fuse = 0;
+  c.f16_mlp = 0;
+  c.f16_pair = 0;
   c.f16_debug_filt = 0;
   c.f16_timing = nullptr;
   launch_aggregate(c, x, W, src, in_ptr, n_nodes, F, out);
@@ -649,6 +671,8 @@ int agd_get_mode(const agd_handle* h) { return h ? h->use_tc : AGD_ERR_INVALID; 
 int agd_set_option(agd_handle* h, const char* name, int value) {
   if (!h || !name) return fail(AGD_ERR_INVALID, "null argument");
   if (std::strcmp(name, "f16_fuse") == 0) h->f16_fuse = value ? 1 : 0;
+  else if (std::strcmp(name, "f16_mlp") == 0) h->f16_mlp = value ? 1 : 0;
+  else if (std::strcmp(name, "f16_pair") == 0) h->f16_pair = value ? 1 : 0;
   else if (std::strcmp(name, "f16_debug_filt") == 0) h->f16_debug_filt = value ? 1 : 0;
   else if (std::strcmp(name, "f16_timing") == 0) {   // diagnostics: 1 = allocate + zero the phase counters, 0 = off
     if (value && !h->f16_timing) {

@@ -49,6 +49,9 @@ struct GinW {              // GINEConv + BatchNorm, gin.py:38-69,112-148
 struct ModelW {
   EncW enc;
   const float *tenc_W1, *tenc_M2, *tenc_C2;            // tcgen05 [hi|lo] images of the encoder matrices
+  const float *henc_W1, *henc_M2, *henc_C2, *henc_sc;  // fp16-split images of the same + inverse weight scales (tc_mlp16.cu)
+  const float *hpg_P1h, *hpg_P1e, *hpg_P2, *hpg_sc;    // ... of the global pair MLP (P1e: unscaled lo)
+  const float *hpl_P1h, *hpl_P1e, *hpl_P2, *hpl_sc;    // ... of the local pair MLP
   const float *tpg_P1h, *tpg_P1e, *tpg_P2;              // ... of the global pair MLP
   const float *tpl_P1h, *tpl_P1e, *tpl_P2;              // ... of the local pair MLP
   const float* sch_emb;   // [100][128], max_norm renorm pre-applied
@@ -91,6 +94,7 @@ struct BatchDev {
   float* filt;                   // [cap][192]  CFConv filters of the current block (conv1 | conv2)
   float *h, *xcat, *agg;         // [N][128], [N][192], [N][192]
   float *gx0, *gx1;              // [N][128] GIN ping-pong
+  float* hmax;                   // [N] per-atom max |h| feeding the pair kernels' per-row scale (AGD_MODE_F16)
   // per-step schedule (device copy)
   float* sched;                  // [n_steps][4] sigma, step_size, noise_scale, use_global
   int sched_cap;
@@ -119,6 +123,8 @@ struct LaunchCtx {
   int use_tc;      // 0: fp32 FFMA tile kernels, 1: tcgen05 3xTF32 everywhere, 2: tcgen05 with 3xFP16 two-slot filter kernels
   int f16_debug_filt;   // fused kernels also write the filter tensor
   unsigned long long* f16_timing;   // diagnostics: per-phase cycle counters of the f16 filter kernels (device, 64 values) or nullptr
+  int f16_mlp;     // use_tc == 2: edge encoder on the fp16 two-slot kernels (tc_mlp16.cu)
+  int f16_pair;    // use_tc == 2: pair MLPs on the fp16 two-slot kernels
   int f16_fuse;    // use_tc == 2: CFConv aggregation fused into the filter kernels (no filt tensor, no aggregate kernel)
   float cutoff;
   int smooth;
@@ -149,6 +155,10 @@ void launch_encoder_global_tc(const LaunchCtx& c, const BatchDev& b, const Model
 void launch_encoder_local_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos);
 void launch_pair_global_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w);
 void launch_pair_local_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* h_local);
+void launch_encoder_global_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& w);   // tc_mlp16.cu
+void launch_encoder_local_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos);
+void launch_pair_global_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& w);
+void launch_pair_local_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* h_local);
 void launch_schnet_node_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);   // tc_node.cu
 void launch_gin_layer_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int layer, const float* x_in, float* x_out);
 void launch_aggregate(const LaunchCtx& c, const float* x, const float* W, const int* src, const int* in_ptr, int n_nodes,

@@ -305,6 +305,7 @@ class DualEncoderEpsNetwork(nn.Module):
         self._handle = None
         self._handle_device = None
         self._packed_version = None
+        self.range_fallbacks = 0      # calls re-run on the 3xTF32 kernels because an activation left the fp16-split range
 
     # ------------------------------------------------------------------ native plumbing
     def _device(self) -> torch.device:
@@ -485,6 +486,7 @@ class DualEncoderEpsNetwork(nn.Module):
         fn = lib.agd_build_edges if build_only else lib.agd_forward
         _lib.check(fn(self._native_handle(), nb.handle, _ptr(pos), C.byref(out), self._stream()))
         if not build_only and self._range_exceeded(nb):
+            self.range_fallbacks += 1
             with self._mode(_lib.MODE_TF32):     # fp16-split range left: same call on the 3xTF32 kernels
                 _lib.check(fn(self._native_handle(), nb.handle, _ptr(pos), C.byref(out), self._stream()))
         E = int(ne.item())
@@ -538,6 +540,7 @@ class DualEncoderEpsNetwork(nn.Module):
             torch.cuda.synchronize(dev)
             _lib.check(lib.agd_forward_edges(self._native_handle(), nb.handle, _ptr(pos), C.byref(es), C.byref(out), self._stream()))
             if self._range_exceeded(nb):
+                self.range_fallbacks += 1
                 with self._mode(_lib.MODE_TF32):
                     _lib.check(lib.agd_forward_edges(self._native_handle(), nb.handle, _ptr(pos), C.byref(es), C.byref(out),
                                                      self._stream()))
@@ -673,6 +676,7 @@ class DualEncoderEpsNetwork(nn.Module):
                         rc = lib.agd_sample(self._native_handle(), nb.handle, _ptr(pos_c), C.byref(p), C.byref(nan_step),
                                             self._stream())
                         if rc == _lib.AGD_ERR_RANGE:
+                            self.range_fallbacks += 1
                             pos_c.copy_(backup)
                             with self._mode(_lib.MODE_TF32):
                                 rc = lib.agd_sample(self._native_handle(), nb.handle, _ptr(pos_c), C.byref(p), C.byref(nan_step),

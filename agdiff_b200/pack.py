@@ -59,7 +59,14 @@ def umma_image(W: np.ndarray) -> np.ndarray:
     return out
 
 
-def umma_image_f16(W: np.ndarray, lo_shift: int = 11):
+def f16_scale_exp(*mats) -> int:
+    """power-of-two exponent e with max|w| * 2^e in [2^13, 2^14) over all the given matrices (0 for all-zero input)"""
+    m = max(float(np.abs(np.asarray(W, dtype=np.float64).astype(np.float32)).max()) for W in mats)
+    e = 0 if not np.isfinite(m) or m == 0.0 else 13 - int(np.floor(np.log2(m)))
+    return max(-100, min(100, e))
+
+
+def umma_image_f16(W: np.ndarray, lo_shift: int = 11, scale_exp=None):
     """tcgen05 kind::f16 B-operand image of a Linear weight W[N][K] for the fp16-split kernels (csrc/tc_filter16.cu).
     The fp32 weight is scaled by a power of two s (max|w|*s in [2^13, 2^14): every part stays a NORMAL fp16 number for
     weights down to 2^-17 of the largest) and split into hi = rn_f16(w*s), lo' = rn_f16((w*s - hi) * 2^lo_shift); each
@@ -68,9 +75,7 @@ def umma_image_f16(W: np.ndarray, lo_shift: int = 11):
     w32 = np.ascontiguousarray(W, dtype=np.float64).astype(np.float32)
     N, K = w32.shape
     assert K % 64 == 0 and N % 8 == 0
-    m = float(np.abs(w32).max())
-    e = 0 if not np.isfinite(m) or m == 0.0 else 13 - int(np.floor(np.log2(m)))
-    e = max(-100, min(100, e))
+    e = f16_scale_exp(w32) if scale_exp is None else int(scale_exp)
     ws = np.ldexp(w32, e).astype(np.float32)                 # exact (power of two)
     hi = ws.astype(np.float16)
     lo = np.ldexp(ws - hi.astype(np.float32), lo_shift).astype(np.float16)
@@ -104,6 +109,11 @@ def fold_state_dict(sd: Dict[str, torch.Tensor], num_convs: int, num_convs_local
     out["tenc.M2"] = umma_image(C1[:, :H] @ L2)
     out["tenc.C2"] = umma_image(C2)
     out["enc.c2b"] = cb2
+    hsc = np.zeros(4)
+    out["henc.W1"], hsc[0] = umma_image_f16(L1[:, :H], lo_shift)
+    out["henc.M2"], hsc[1] = umma_image_f16(C1[:, :H] @ L2, lo_shift)
+    out["henc.C2"], hsc[2] = umma_image_f16(C2, lo_shift)
+    out["henc.sc"] = hsc
 
     g = "encoder_global."
     emb = _f64(sd[g + "embedding.weight"]).copy()
@@ -168,6 +178,15 @@ def fold_state_dict(sd: Dict[str, torch.Tensor], num_convs: int, num_convs_local
         out[tp + "P1h"] = umma_image(W0[:, :H])
         out[tp + "P1e"] = umma_image(W0[:, H:] @ C2 if merged else W0[:, H:])
         out[tp + "P2"] = umma_image(_f64(sd[pre + "layers.1.weight"]))
+        hp, hsc = "h" + p, np.zeros(4)
+        # both halves of layers.0 accumulate into ONE tensor-core accumulator: common weight scale.  The edge-feature half is
+        # added onto the finished h half, where the scale-input-d fold is not available: unscaled lo parts (operand and weight)
+        P1e = W0[:, H:] @ C2 if merged else W0[:, H:]
+        e1 = f16_scale_exp(W0[:, :H], P1e)
+        out[hp + "P1h"], hsc[0] = umma_image_f16(W0[:, :H], lo_shift, e1)
+        out[hp + "P1e"], hsc[1] = umma_image_f16(P1e, 0, e1)
+        out[hp + "P2"], hsc[2] = umma_image_f16(_f64(sd[pre + "layers.1.weight"]), lo_shift)
+        out[hp + "sc"] = hsc
         out[p + "p2b"] = _f64(sd[pre + "layers.1.bias"])
         out[p + "p3w"] = _f64(sd[pre + "layers.2.weight"])[0]
         out[p + "p3b"] = _f64(sd[pre + "layers.2.bias"])

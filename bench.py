@@ -374,7 +374,8 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, n_conf_total), "gpu_launches": int(launches),
                 "e2e": {"value": e2e, "unit": "conformers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+                "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "range_fallbacks": int(model.range_fallbacks)}   # sampler calls re-run on the 3xTF32 kernels (0 expected)
         line.update(extra)
         print(json.dumps(line))
     if world > 1:
