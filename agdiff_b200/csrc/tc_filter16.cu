@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
     const float lo_scale = a.scaled ? static_cast<float>(1 << F16_LO_SHIFT) : 1.0f;
     __half2 amax = __floats2half2_rn(0.f, 0.f);
     uint32_t dph = 0, aph = 0, prod_cnt = 0, cons_cnt = 0;
-    const bool issuer = (tid & (F16_GROUP - 1)) == 0;
+    const bool issuer = (gwarp == F16_GWARPS - 1) && lane == 0;   // the group's last warp rarely owns a run: its issue work stays off the aggregation's critical path
     const bool scaled = a.scaled != 0;
     if (issuer && g < cta_tiles) mbar_wait(&bars[0], 0);
 
@@ -333,17 +333,24 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
         s_src[my_row] = valid ? __ldg(a.e_src + r) : 0;
         s_dst[my_row] = valid ? __ldg(a.e_dst + r) : -1;
       }
-      wait_st();
-      fence_before_sync();
-      group_sync(1 + g, F16_GROUP);
+      // layer 1 of this tile: with FUSE only the CTA's first tile of each slot is issued here - later ones are issued during the
+      // previous tile's aggregation (below), which hides the whole MMA window
+      const bool issue_here = !FUSE || j == g;
+      if (issue_here) {
+        wait_st();
+        fence_before_sync();
+      }
+      group_sync(1 + g, F16_GROUP);   // publishes s_src / s_dst
       tick(0);
-      mbar_arrive(a_ready);
-      if (issuer) {
-        mbar_wait(a_ready, aph);
-        aph ^= 1u;
-        fence_after_sync();
-        issue_3xf16<HID, F>(slot, smem_u32(w1), W1_HALF, scaled);
-        mma_commit(d_ready);
+      if (issue_here) {
+        mbar_arrive(a_ready);
+        if (issuer) {
+          mbar_wait(a_ready, aph);
+          aph ^= 1u;
+          fence_after_sync();
+          issue_3xf16<HID, F>(slot, smem_u32(w1), W1_HALF, scaled);
+          mma_commit(d_ready);
+        }
       }
       const float cw = valid ? len_cur : 0.f;   // envelope * distance weight of this thread's row (edge_weight_kernel)
       // run structure of this tile (FUSE; every warp computes the same masks while layer 1 runs)
@@ -417,38 +424,66 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_filter16_kernel(const TcF16
         len_cur = pre_len;
       }
       if (FUSE) {
-        // two column halves per thread are staged as 64-column half-tiles: pass p holds filter columns [64p, 64p+64)
-#pragma unroll 1
-        for (int pass = 0; pass < F / 64; ++pass) {
-          const int n0 = pass * 64 + half * 32;
+        // the filter tile is staged as 64-column half-tiles: pass p holds filter columns [64p, 64p+64)
+        auto stage_half = [&](const uint32_t (&v)[32], int n0) {
           float4* dstW = reinterpret_cast<float4*>(s_W + my_row * LDS_W + half * 32);
-          {
-            uint32_t v[32];
-            tmem_ld32(trow + C16_D + n0, v);
-            wait_ld();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int n = n0 + q * 4;
-              float4 o;
-              o.x = fmaf(__uint_as_float(v[q * 4 + 0]), inv2, s_b2[n + 0]) * cw;
-              o.y = fmaf(__uint_as_float(v[q * 4 + 1]), inv2, s_b2[n + 1]) * cw;
-              o.z = fmaf(__uint_as_float(v[q * 4 + 2]), inv2, s_b2[n + 2]) * cw;
-              o.w = fmaf(__uint_as_float(v[q * 4 + 3]), inv2, s_b2[n + 3]) * cw;
-              dstW[q] = o;
-              if (a.debug_filt && valid) *reinterpret_cast<float4*>(a.filt + r * 192 + a.col0 + n) = o;
-            }
+          for (int q = 0; q < 8; ++q) {
+            const int n = n0 + q * 4;
+            float4 o;
+            o.x = fmaf(__uint_as_float(v[q * 4 + 0]), inv2, s_b2[n + 0]) * cw;
+            o.y = fmaf(__uint_as_float(v[q * 4 + 1]), inv2, s_b2[n + 1]) * cw;
+            o.z = fmaf(__uint_as_float(v[q * 4 + 2]), inv2, s_b2[n + 2]) * cw;
+            o.w = fmaf(__uint_as_float(v[q * 4 + 3]), inv2, s_b2[n + 3]) * cw;
+            dstW[q] = o;
+            if (a.debug_filt && valid) *reinterpret_cast<float4*>(a.filt + r * 192 + a.col0 + n) = o;
           }
-          if (pass == 0) {   // next tile's operand rows (prefetched during layer 2) -> TMEM; frees the 64 prefetch registers
-            stage_operand();
-            len_cur = pre_len;
-          }
-          group_sync(1 + g, F16_GROUP);    // half-tile complete
-          tick(4);
+        };
+        auto aggregate = [&](int pass) {
           aggregate_half<F>(a, rc, s_W, s_src, s_dst, s_runs, pass, s_carry + g * 128, s_carry + (1 - g) * 128,
                             &bars[5 + 2 * g + pass], &bars[9 + 2 * g + pass], &bars[5 + 2 * (1 - g) + pass],
                             &bars[9 + 2 * (1 - g) + pass], prod_cnt, cons_cnt, gwarp, lane);
+        };
+        {
+          uint32_t v[32];
+          tmem_ld32(trow + C16_D + half * 32, v);
+          wait_ld();
+          stage_half(v, half * 32);
+        }
+        stage_operand();   // next tile's operand rows (prefetched during layer 2) -> TMEM; frees the 64 prefetch registers
+        len_cur = pre_len;
+        uint32_t v1[32];   // F = 128: the second half-tile leaves TMEM now, so that the accumulator is free for the next tile
+        if (F == 128) {
+          tmem_ld32(trow + C16_D + 64 + half * 32, v1);
+          wait_ld();
+        }
+        // D is fully read and the next operand is staged: the next tile's layer 1 runs underneath this tile's aggregation
+        const bool next = j + 2 < cta_tiles;
+        if (next) {
+          wait_st();
+          fence_before_sync();
+          mbar_arrive(a_ready);
+        }
+        group_sync(1 + g, F16_GROUP);    // half-tile complete (and every thread of the group has arrived on a_ready)
+        tick(4);
+        if (next && issuer) {
+          mbar_wait(a_ready, aph);
+          aph ^= 1u;
+          fence_after_sync();
+          issue_3xf16<HID, F>(slot, smem_u32(w1), W1_HALF, scaled);
+          mma_commit(d_ready);
+        }
+        aggregate(0);
+        tick(5);
+        group_sync(1 + g, F16_GROUP);    // half-tile consumed
+        tick(6);
+        if (F == 128) {
+          stage_half(v1, 64 + half * 32);
+          group_sync(1 + g, F16_GROUP);
+          tick(4);
+          aggregate(1);
           tick(5);
-          group_sync(1 + g, F16_GROUP);    // half-tile consumed (s_W, and after the last pass s_src / s_dst / s_runs, may be rewritten)
+          group_sync(1 + g, F16_GROUP);  // s_W, s_src / s_dst / s_runs may be rewritten
           tick(6);
         }
         if (rc.carry_out) ++prod_cnt;      // every warp of the group counts the same hand-offs
