@@ -97,6 +97,39 @@ def test_pack_layout_follows_library_slots():
         pack.pack(f, names, [s + 1 for s in sizes])
 
 
+@pytest.mark.parametrize("N,K,scale", [(128, 128, 0.09), (64, 128, 3.0e-4), (64, 64, 40.0)])
+def test_fp16_split_weight_image(N, K, scale):
+    """pack.umma_image_f16: hi + lo' * 2^-S reproduces the power-of-two-scaled fp32 weight to 2^-22, every part is a NORMAL fp16
+    number for weights down to 2^-17 of the largest, and element (n, k) sits where the K-major SWIZZLE_128B descriptor of
+    csrc/tc16_common.cuh expects it (64-half atoms, 16-byte chunk c of row n at chunk c ^ (n % 8))."""
+    rng = np.random.default_rng(3)
+    W = (rng.standard_normal((N, K)) * scale).astype(np.float64)
+    W[0, 0] = 0.0
+    for S in (11, 0):
+        img, inv = pack.umma_image_f16(W, S)
+        assert img.dtype == np.float32 and img.size == N * K
+        halves = img.view(np.float16)
+        s = 1.0 / inv
+        assert 2.0 ** 13 <= np.abs(W.astype(np.float32)).max() * s < 2.0 ** 14
+        n, k = np.arange(N)[:, None], np.arange(K)[None, :]
+        off = (k // 64) * (N * 64) + n * 64 + ((((k % 64) // 8) ^ (n % 8)) * 8) + (k % 8)
+        hi = halves[off].astype(np.float64)
+        lo = halves[N * K + off].astype(np.float64)
+        ws = W.astype(np.float32).astype(np.float64) * s
+        err = np.abs(hi + lo * 2.0 ** -S - ws)
+        assert float((err / np.maximum(np.abs(ws), 2.0 ** -3)).max()) <= 2.0 ** -21
+        big = np.abs(ws) >= 2.0 ** -3                      # = 2^-17 of the largest weight or more
+        assert np.all(np.abs(hi[big]) >= 2.0 ** -14)       # hi normal
+        if S == 11:
+            nz = big & (lo != 0)
+            assert np.all(np.abs(lo[nz]) >= 2.0 ** -14)    # lo' normal thanks to the 2^S pre-scale
+    # a common exponent makes two matrices share one accumulator scale (pair MLP, layers.0)
+    e = pack.f16_scale_exp(W, 8 * W)
+    _, inv_a = pack.umma_image_f16(W, 11, e)
+    _, inv_b = pack.umma_image_f16(8 * W, 0, e)
+    assert inv_a == inv_b == 2.0 ** -e
+
+
 def test_bond_order_host_matches_reference_golden():
     g = golden("bond_order_ext")
     mols = synth.qm9_like(3, seed=4) + synth.drugs_like(2, seed=8, force_max=False) + [synth.alanine_dipeptide()]
