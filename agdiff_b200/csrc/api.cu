@@ -20,6 +20,7 @@ void set_tc_mlp_attributes();
 void set_tc_node_attributes();
 void set_tc16_attributes();
 void set_tc_mlp16_attributes();
+void set_tc_node16_attributes();
 }  // namespace agd
 
 using namespace agd;
@@ -55,6 +56,7 @@ struct agd_handle {
   int f16_fuse = 1;
   int f16_mlp = 1;
   int f16_pair = 1;
+  int f16_node = 1;
   int f16_debug_filt = 0;
   unsigned long long* f16_timing = nullptr;
   int use_tc = 2;   // AGD_TC_FILTERS / agd_set_mode: 0 FFMA, 1 tcgen05 3xTF32, 2 tcgen05 + 3xFP16 filter kernels
@@ -113,6 +115,9 @@ static void build_slots(agd_handle* h) {
     add(p + "hF1a", 128 * 128, &b.hF1a); add(p + "hF2a", 128 * 128, &b.hF2a);
     add(p + "hF1b", 64 * 128, &b.hF1b);   add(p + "hF2b", 64 * 64, &b.hF2b);
     add(p + "hsc", 4, &b.hsc);
+    add(p + "hL2a", 128 * 128, &b.hL2a); add(p + "hLINa", 128 * 128, &b.hLINa); add(p + "hL2b", 128 * 64, &b.hL2b);
+    add(p + "hLINb", 128 * 128, &b.hLINb); add(p + "hA1", 64 * 128, &b.hA1);
+    add(p + "hL1a", 128 * 128, &b.hL1a); add(p + "hL1b", 64 * 128, &b.hL1b); add(p + "hnsc", 8, &b.hnsc);
   }
   auto add_pair = [&](const std::string& p, PairW& q) {
     add(p + "P1h", H * H, &q.P1h); add(p + "P1e", H * H, &q.P1e); add(p + "p1b", H, &q.p1b);
@@ -142,6 +147,7 @@ static LaunchCtx make_ctx(agd_handle* h) {
   c.f16_fuse = h->f16_fuse;
   c.f16_mlp = (h->use_tc == 2) ? h->f16_mlp : 0;
   c.f16_pair = (h->use_tc == 2) ? h->f16_pair : 0;
+  c.f16_node = (h->use_tc == 2) ? h->f16_node : 0;
   c.f16_debug_filt = h->f16_debug_filt;
   c.f16_timing = h->f16_timing;
   c.cutoff = h->cfg.cutoff;
@@ -191,11 +197,15 @@ static void run_global_branch(const LaunchCtx& c, const BatchDev& b, const Model
   else if (c.use_tc) launch_encoder_global_tc(c, b, w);
   else launch_encoder_global(c, b, w);
   if (c.use_tc == 2) launch_edge_weights_f16(c, b, w);
-  if (c.use_tc) launch_schnet_node_tc(c, b, w, -1); else launch_schnet_node(c, b, w, -1);
+  if (c.f16_node) launch_schnet_node_f16(c, b, w, -1);
+  else if (c.use_tc) launch_schnet_node_tc(c, b, w, -1);
+  else launch_schnet_node(c, b, w, -1);
   for (int k = 0; k < c.num_convs; ++k) {
     launch_filters(c, b, w, k);
     if (!((c.use_tc == 1 && filters_tc_fused()) || (c.use_tc == 2 && c.f16_fuse))) launch_aggregate(c, b.xcat, b.filt, b.e_src, b.in_ptr, b.n_atoms, 192, b.agg);
-    if (c.use_tc) launch_schnet_node_tc(c, b, w, k); else launch_schnet_node(c, b, w, k);
+    if (c.f16_node) launch_schnet_node_f16(c, b, w, k);
+    else if (c.use_tc) launch_schnet_node_tc(c, b, w, k);
+    else launch_schnet_node(c, b, w, k);
   }
   if (c.f16_pair) launch_pair_global_f16(c, b, w);
   else if (c.use_tc) launch_pair_global_tc(c, b, w);
@@ -234,9 +244,11 @@ int agd_create(const agd_config* cfg, agd_handle** out) {
   set_tc_node_attributes();
   set_tc16_attributes();
   set_tc_mlp16_attributes();
+  set_tc_node16_attributes();
   h->f16_fuse = f16_fuse_default();
   if (const char* e = std::getenv("AGD_F16_MLP")) h->f16_mlp = (e[0] != '0');
   if (const char* e = std::getenv("AGD_F16_PAIR")) h->f16_pair = (e[0] != '0');
+  if (const char* e = std::getenv("AGD_F16_NODE")) h->f16_node = (e[0] != '0');
   if (const char* e = std::getenv("AGD_TC_FILTERS")) h->use_tc = (e[0] == '0') ? 0 : (e[0] == '1') ? 1 : 2;
   CUDA_TRY(cudaGetLastError());
   *out = h;
@@ -620,6 +632,7 @@ int agd_op_cfconv_aggregate(const float* x, const float* W, const int32_t* src, 
   c.f16_fuse = 0;
   c.f16_mlp = 0;
   c.f16_pair = 0;
+  c.f16_node = 0;
   c.f16_debug_filt = 0;
   c.f16_timing = nullptr;
   launch_aggregate(c, x, W, src, in_ptr, n_nodes, F, out);
@@ -673,6 +686,7 @@ int agd_set_option(agd_handle* h, const char* name, int value) {
   if (std::strcmp(name, "f16_fuse") == 0) h->f16_fuse = value ? 1 : 0;
   else if (std::strcmp(name, "f16_mlp") == 0) h->f16_mlp = value ? 1 : 0;
   else if (std::strcmp(name, "f16_pair") == 0) h->f16_pair = value ? 1 : 0;
+  else if (std::strcmp(name, "f16_node") == 0) h->f16_node = value ? 1 : 0;
   else if (std::strcmp(name, "f16_debug_filt") == 0) h->f16_debug_filt = value ? 1 : 0;
   else if (std::strcmp(name, "f16_timing") == 0) {   // diagnostics: 1 = allocate + zero the phase counters, 0 = off
     if (value && !h->f16_timing) {

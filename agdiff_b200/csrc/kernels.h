@@ -35,6 +35,8 @@ struct BlkW {              // InteractionBlock k, schnet.py:165-216 (+ scaling m
   const float *tL1a, *tL1b, *tL2a, *tL2b, *tLINa, *tLINb, *tA1;   // ... of the node-side Linears
   const float *hF1a, *hF2a, *hF1b, *hF2b;    // fp16-split operand images of the filter nets: [hi | lo'] packed halves (tc_filter16.cu)
   const float* hsc;                          // inverse power-of-two weight scales of hF1a, hF2a, hF1b, hF2b
+  const float *hL2a, *hLINa, *hL2b, *hLINb, *hA1, *hL1a, *hL1b;   // fp16-split images of the node-side Linears (tc_node16.cu)
+  const float* hnsc;                         // their inverse scales [L2a, LINa, L2b, LINb, A1, L1a, L1b, -]
 };
 struct PairW {             // grad_{global,local}_dist_mlp, common.py:86-103 on [h_row*h_col, edge_attr]
   const float *P1h, *P1e, *p1b;   // layers.0 split: [128][128] on h_row*h_col, [128][128] on g2 (global, merged) / edge_attr (local)
@@ -125,6 +127,7 @@ struct LaunchCtx {
   unsigned long long* f16_timing;   // diagnostics: per-phase cycle counters of the f16 filter kernels (device, 64 values) or nullptr
   int f16_mlp;     // use_tc == 2: edge encoder on the fp16 two-slot kernels (tc_mlp16.cu)
   int f16_pair;    // use_tc == 2: pair MLPs on the fp16 two-slot kernels
+  int f16_node;    // use_tc == 2: SchNet node chain on the fp16 kernel with double-buffered weight streaming (tc_node16.cu)
   int f16_fuse;    // use_tc == 2: CFConv aggregation fused into the filter kernels (no filt tensor, no aggregate kernel)
   float cutoff;
   int smooth;
@@ -159,6 +162,7 @@ void launch_encoder_global_f16(const LaunchCtx& c, const BatchDev& b, const Mode
 void launch_encoder_local_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos);
 void launch_pair_global_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& w);
 void launch_pair_local_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* h_local);
+void launch_schnet_node_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);   // tc_node16.cu
 void launch_schnet_node_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);   // tc_node.cu
 void launch_gin_layer_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int layer, const float* x_in, float* x_out);
 void launch_aggregate(const LaunchCtx& c, const float* x, const float* W, const int* src, const int* in_ptr, int n_nodes,

@@ -394,6 +394,19 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
         const float4 self = __ldg(reinterpret_cast<const float4*>(a.x_in + node * HID) + lane);
         const int e0 = __ldg(a.in_ptr + node), e1 = __ldg(a.in_ptr + node + 1);
         int e = e0;
+        for (; e + 8 <= e1; e += 8) {   // 8 edges in flight: the gather is latency-bound (L2 / HBM round trips), not bandwidth-bound
+          float4 xv[8], ev[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            xv[u] = __ldg(reinterpret_cast<const float4*>(a.x_in + (size_t)__ldg(a.src + e + u) * HID) + lane);
+            ev[u] = __ldcs(reinterpret_cast<const float4*>(a.ea + (size_t)(e + u) * HID) + lane);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            acc.x += relu_(xv[u].x + ev[u].x); acc.y += relu_(xv[u].y + ev[u].y);
+            acc.z += relu_(xv[u].z + ev[u].z); acc.w += relu_(xv[u].w + ev[u].w);
+          }
+        }
         for (; e + 4 <= e1; e += 4) {
           float4 xv[4], ev[4];
 #pragma unroll

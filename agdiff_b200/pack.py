@@ -150,6 +150,17 @@ def fold_state_dict(sd: Dict[str, torch.Tensor], num_convs: int, num_convs_local
             Wm = (_f64(sd[cp + "nn.0.weight"]) @ C2) if tag.startswith("F1") else _f64(sd[cp + "nn.2.weight"])
             out[p + "h" + tag], hsc[j] = umma_image_f16(Wm, lo_shift)
         out[p + "hsc"] = hsc
+        nsc = np.zeros(8)
+        for c, tag in ((1, "a"), (2, "b")):
+            cp = "%sconv%d." % (ip, c)
+            W2, _ = _fold_bn(sd, cp + "lin2", cp + "norm2")                  # [K][N]
+            out[p + "hL2" + tag], nsc[0 if c == 1 else 2] = umma_image_f16(W2.T, lo_shift)
+            W1, _ = _fold_bn(sd, cp + "lin1", cp + "norm1")
+            out[p + "hL1" + tag], nsc[5 if c == 1 else 6] = umma_image_f16(W1.T, lo_shift)
+        out[p + "hLINa"], nsc[1] = umma_image_f16(_f64(sd[ip + "lin.weight"])[:, :128], lo_shift)
+        out[p + "hLINb"], nsc[3] = umma_image_f16(_f64(sd[ip + "lin.weight"])[:, 128:], lo_shift)
+        out[p + "hA1"], nsc[4] = umma_image_f16(_f64(sd[ip + "attention.0.weight"]), lo_shift)
+        out[p + "hnsc"] = nsc
         out[p + "LIN"] = _f64(sd[ip + "lin.weight"]).T
         out[p + "tLINa"] = umma_image(_f64(sd[ip + "lin.weight"])[:, :128])
         out[p + "tLINb"] = umma_image(_f64(sd[ip + "lin.weight"])[:, 128:])
