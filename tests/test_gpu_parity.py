@@ -225,6 +225,42 @@ def test_forward_with_supplied_edges_and_without_radius():
         assert_close(out[1], ref[1], what="edge_inv_local (no radius)", extra_atol=1e-4)
 
 
+def test_supplied_complete_graph_long_runs():
+    """Caller-supplied edge lists may have any in-degree: a COMPLETE graph on a 181-atom molecule gives every destination 180
+    in-edges - more than one 128-edge tile, so inside the fused CFConv kernel a destination's run spans up to three tiles and its
+    partial sum is handed from slot to slot twice.  Result: bit-identical to the unfused path, and within the parity bar of the oracle."""
+    m, sd = _cuda_model("drugs", 2021, 6)
+    _settle(m)
+    cfg = CONFIGS["drugs"]
+    mols = synth.drugs_like(4, seed=21, force_max=True)
+    z, bi, bt, b, G = graph.collate(mols, 1)
+    assert int(torch.bincount(b).max()) == 181
+    gen = torch.Generator().manual_seed(2)
+    pos = torch.randn(z.numel(), 3, generator=gen) * 2.0
+    N = z.numel()
+    same = b[:, None] == b[None, :]
+    same.fill_diagonal_(False)
+    ei = same.nonzero().t().contiguous()                                   # every ordered pair inside a molecule
+    key = ei[0] * N + ei[1]
+    bkey = bi[0] * N + bi[1]
+    et = torch.zeros(ei.size(1), dtype=torch.long)
+    pos_in = torch.searchsorted(key, bkey)
+    et[pos_in] = bt                                                        # bonds keep their types, the rest are radius-type edges
+    elen = O.edge_lengths(pos, ei).unsqueeze(-1)
+    args = (z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), None)
+    kw = dict(edge_index=ei.to(DEV), edge_type=et.to(DEV), edge_length=elen.to(DEV), return_edges=True)
+    m.set_option("f16_fuse", 1)
+    out_f = m(*args, **kw)
+    m.set_option("f16_fuse", 0)
+    out_u = m(*args, **kw)
+    m.set_option("f16_fuse", 1)
+    assert torch.equal(out_f[0], out_u[0]) and torch.equal(out_f[1], out_u[1])
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, z, pos, bi, bt, b, edges=(ei, et, elen))
+    assert_close(out_f[0], ref[0], what="edge_inv_global (complete graph)", extra_atol=1e-5)
+    assert_close(out_f[1], ref[1], what="edge_inv_local (complete graph)", extra_atol=1e-4)
+
+
 def test_state_dict_roundtrip_and_renorm_side_effect():
     m, sd = _cuda_model("qm9", 2021, 8)
     m2, _ = _cuda_model("qm9", 1, 0)
