@@ -20,7 +20,7 @@ z, bi, bt, b, G = graph.collate(mols, 2)
 dev = "cuda:0"
 pos = (torch.randn(z.numel(), 3, generator=torch.Generator().manual_seed(0)) * 1.5).to(dev)
 args = (z.to(dev), pos, bi.to(dev), bt.to(dev), b.to(dev), G)
-for name, t_start, n in (("global", 1000, 100), ("local-only", 5000, 300)):
+for name, t_start, n in (("global", 1500, 480), ("local-only", 5000, 1600)):   # long enough to amortise graph capture + instantiation
     for graph_on in (True, False):
         kw = dict(SAMPLER, n_steps=n, t_start=t_start, scale_init=False, return_traj=False, seed=1, use_cuda_graph=graph_on)
         m.langevin_dynamics_sample_diffusion(*args, **dict(kw, n_steps=10))
