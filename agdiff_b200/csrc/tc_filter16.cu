@@ -144,37 +144,24 @@ __device__ __forceinline__ void aggregate_half(const TcF16Args& a, const RunCtx&
         acc.y = fmaf(xv[u].y, wv[u].y, acc.y);
       }
     }
-    for (; row + 8 <= e; row += 8) {
-      float2 xv[8], wv[8];
+    if (row < e) {   // remainder (1..15 rows) as ONE predicated batch: a tail walked row by row costs an L2 round trip per row
+      const int n = e - row;
+      float2 xv[16], wv[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        xv[u] = __ldg(reinterpret_cast<const float2*>(a.xcat + (size_t)s_src[row + u] * 192 + colg));
-        wv[u] = *reinterpret_cast<const float2*>(s_W + (row + u) * LDS_W + 2 * lane);
+      for (int u = 0; u < 16; ++u) {
+        xv[u] = make_float2(0.f, 0.f);
+        wv[u] = make_float2(0.f, 0.f);
+        if (u < n) {
+          xv[u] = __ldg(reinterpret_cast<const float2*>(a.xcat + (size_t)s_src[row + u] * 192 + colg));
+          wv[u] = *reinterpret_cast<const float2*>(s_W + (row + u) * LDS_W + 2 * lane);
+        }
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        acc.x = fmaf(xv[u].x, wv[u].x, acc.x);
-        acc.y = fmaf(xv[u].y, wv[u].y, acc.y);
+      for (int u = 0; u < 16; ++u) {
+        const float ax = fmaf(xv[u].x, wv[u].x, acc.x), ay = fmaf(xv[u].y, wv[u].y, acc.y);
+        acc.x = (u < n) ? ax : acc.x;
+        acc.y = (u < n) ? ay : acc.y;
       }
-    }
-    for (; row + 4 <= e; row += 4) {
-      float2 xv[4], wv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        xv[u] = __ldg(reinterpret_cast<const float2*>(a.xcat + (size_t)s_src[row + u] * 192 + colg));
-        wv[u] = *reinterpret_cast<const float2*>(s_W + (row + u) * LDS_W + 2 * lane);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        acc.x = fmaf(xv[u].x, wv[u].x, acc.x);
-        acc.y = fmaf(xv[u].y, wv[u].y, acc.y);
-      }
-    }
-    for (; row < e; ++row) {
-      const float2 xv = __ldg(reinterpret_cast<const float2*>(a.xcat + (size_t)s_src[row] * 192 + colg));
-      const float2 wv = *reinterpret_cast<const float2*>(s_W + row * LDS_W + 2 * lane);
-      acc.x = fmaf(xv.x, wv.x, acc.x);
-      acc.y = fmaf(xv.y, wv.y, acc.y);
     }
     if (k == rc.n_runs - 1 && rc.carry_out) {
       tc::mbar_wait(empty_mine, (prod_cnt & 1u) ^ 1u);   // the previous carry of this group (same pass) was consumed

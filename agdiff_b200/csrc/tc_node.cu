@@ -407,23 +407,25 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
             acc.z += relu_(xv[u].z + ev[u].z); acc.w += relu_(xv[u].w + ev[u].w);
           }
         }
-        for (; e + 4 <= e1; e += 4) {
-          float4 xv[4], ev[4];
+        if (e < e1) {   // remainder (1..7 edges) as one predicated batch instead of one round trip per edge
+          const int n = e1 - e;
+          float4 xv[8], ev[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            xv[u] = __ldg(reinterpret_cast<const float4*>(a.x_in + (size_t)__ldg(a.src + e + u) * HID) + lane);
-            ev[u] = __ldcs(reinterpret_cast<const float4*>(a.ea + (size_t)(e + u) * HID) + lane);
+          for (int u = 0; u < 8; ++u) {
+            xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ev[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (u < n) {
+              xv[u] = __ldg(reinterpret_cast<const float4*>(a.x_in + (size_t)__ldg(a.src + e + u) * HID) + lane);
+              ev[u] = __ldcs(reinterpret_cast<const float4*>(a.ea + (size_t)(e + u) * HID) + lane);
+            }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            acc.x += relu_(xv[u].x + ev[u].x); acc.y += relu_(xv[u].y + ev[u].y);
-            acc.z += relu_(xv[u].z + ev[u].z); acc.w += relu_(xv[u].w + ev[u].w);
+          for (int u = 0; u < 8; ++u) {
+            if (u < n) {
+              acc.x += relu_(xv[u].x + ev[u].x); acc.y += relu_(xv[u].y + ev[u].y);
+              acc.z += relu_(xv[u].z + ev[u].z); acc.w += relu_(xv[u].w + ev[u].w);
+            }
           }
-        }
-        for (; e < e1; ++e) {
-          const float4 xv = __ldg(reinterpret_cast<const float4*>(a.x_in + (size_t)__ldg(a.src + e) * HID) + lane);
-          const float4 ev = __ldcs(reinterpret_cast<const float4*>(a.ea + (size_t)e * HID) + lane);
-          acc.x += relu_(xv.x + ev.x); acc.y += relu_(xv.y + ev.y); acc.z += relu_(xv.z + ev.z); acc.w += relu_(xv.w + ev.w);
         }
         acc.x = fmaf(ope, self.x, acc.x); acc.y = fmaf(ope, self.y, acc.y);
         acc.z = fmaf(ope, self.z, acc.z); acc.w = fmaf(ope, self.w, acc.w);
