@@ -17,12 +17,17 @@
 //
 // Pipeline (one CTA per SM, 512 threads, 512 TMEM columns = 2 slots x [D 128 | A_hi 64 | A_lo 64]):
 //   * both layers' weight images (hi | lo', K-major SWIZZLE_128B, <= 128 KB) are bulk-copied into shared memory ONCE;
-//   * warps 0-7 own slot 0, warps 8-15 slot 1: each group stages its tile's operand rows into TMEM (tcgen05.st), runs
-//     the SSP epilogue TMEM -> registers -> TMEM and the output epilogue TMEM -> HBM, and signals "operand ready" on an
-//     mbarrier; thread (quad q, lane l, half h) owns tile row 32q+l and one half of the columns;
-//   * the group's first thread is its MMA issuer: once all 256 threads have arrived it issues the layer's 3 x K/16
-//     tcgen05.mma.kind::f16 (M=128, N=F, K=16, A from TMEM) and commits to the slot's "accumulator ready" mbarrier.
-//     While one group runs an epilogue the tensor core works on the other slot.
+//   * warps 0-7 own slot 0, warps 8-15 slot 1; thread (quad q, lane l, half h) of a group owns tile row 32q+l and one half
+//     of the columns.  The operand rows come pre-split from the encoder ("g2h", tc_common.cuh): they are prefetched into
+//     registers during the previous tile's layer 2 and go straight into TMEM (tcgen05.st) - no ALU work;
+//   * lane 0 of the group's last warp is its MMA issuer: once all 256 threads have arrived on the slot's "operand ready"
+//     mbarrier it issues the layer's 3 x K/16 tcgen05.mma.kind::f16 (M=128, N=F, K=16, A from TMEM) and commits to the
+//     slot's "accumulator ready" mbarrier.  While one group runs an epilogue the tensor core works on the other slot;
+//   * epilogue 1: TMEM -> registers, bias + ShiftedSoftplus on the SFU, split, -> TMEM (operand of layer 2);
+//   * epilogue 2 (FUSE): the filter tile is staged in shared memory as 64-column half-tiles and reduced per destination
+//     (aggregate_half below); before that the accumulator is drained and the NEXT tile's layer 1 is issued, so that it runs
+//     underneath the aggregation.  Without FUSE (A/B path, tests) the tile is written to `filt` for cfconv_aggregate_kernel.
+// The envelope x distance-MLP weight cw_e of every edge and layer comes from edge_weight_kernel (once per evaluation).
 #include <cuda_fp16.h>
 
 #include <cstdlib>

@@ -197,8 +197,14 @@ int64_t agd_launch_count(const agd_handle* h);
 enum { AGD_MODE_FFMA = 0, AGD_MODE_TF32 = 1, AGD_MODE_F16 = 2 };
 int agd_set_mode(agd_handle* h, int mode);
 int agd_get_mode(const agd_handle* h);
-/* tuning / A-B switches.  "f16_fuse" (default 1, env AGD_F16_FUSE): in AGD_MODE_F16 the CFConv aggregation runs inside the
- * filter kernels (same sums in the same order as the stand-alone aggregate kernel, bit for bit). */
+/* tuning / A-B switches (AGD_MODE_F16 only; all default to 1 except the diagnostics):
+ *   "f16_fuse"  (env AGD_F16_FUSE)  the CFConv aggregation runs inside the filter kernels (same sums in the same order as the
+ *               stand-alone aggregate kernel, bit for bit); 0: filter tensor to HBM + aggregate kernel
+ *   "f16_mlp"   (env AGD_F16_MLP)   edge encoder on the fp16 two-slot kernels (0: 3xTF32 kernels)
+ *   "f16_pair"  (env AGD_F16_PAIR)  pair MLPs on the fp16 two-slot kernels
+ *   "f16_node"  (env AGD_F16_NODE)  SchNet node chain on the fp16 kernel with double-buffered weight streaming
+ *   "f16_debug_filt" (0)  the fused CFConv kernels also write the filter tensor (tests)
+ *   "f16_timing"     (0)  clock64 phase counters of the CFConv kernels (needs a build with -DAGD_F16_TIMING), agd_debug_timing */
 int agd_set_option(agd_handle* h, const char* name, int value);
 /* 1 if a kernel of the last forward on this batch saw an activation outside the fp16-split range (host sync) */
 int agd_range_flag(agd_batch* b, int32_t* flag_out);
