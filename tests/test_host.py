@@ -226,3 +226,48 @@ def test_oracle_against_live_reference():
     assert torch.equal(r[2], o[2]) and torch.equal(r[3], o[3])
     assert float((r[0] - o[0]).abs().max()) <= 2e-6 * float(r[0].abs().max())
     assert float((r[1] - o[1]).abs().max()) <= 2e-6 * float(r[1].abs().max())
+
+
+def test_reference_checkpoint_loads_without_easydict(tmp_path):
+    """scripts/train.py:218-229 pickles an easydict.EasyDict config next to the state_dict; the loader supplies a stand-in for the
+    absent package, the config keeps attribute access and the state_dict goes into the product model unchanged"""
+    import sys
+    import types
+    from agdiff_b200 import checkpoint
+    assert "easydict" not in sys.modules
+    fake = types.ModuleType("easydict")
+
+    class EasyDict(dict):                       # what the real package pickles: a dict subclass living in module `easydict`
+        def __init__(self, d=None):
+            super().__init__()
+            for k, v in (d or {}).items():
+                self[k] = EasyDict(v) if isinstance(v, dict) else v
+
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError:
+                raise AttributeError(k)
+    EasyDict.__module__ = "easydict"
+    EasyDict.__qualname__ = "EasyDict"
+    fake.EasyDict = EasyDict
+    m = make_model("drugs", 2021, perturb=3)
+    cfg = EasyDict({"model": dict(CONFIGS["drugs"]), "train": {"seed": 2021, "batch_size": 32}})
+    sys.modules["easydict"] = fake
+    try:
+        torch.save({"config": cfg, "model": m.state_dict(), "iteration": 5000, "avg_val_loss": 0.1}, tmp_path / "5000.pt")
+    finally:
+        del sys.modules["easydict"]
+    ckpt = checkpoint.load_checkpoint(str(tmp_path / "5000.pt"))
+    assert "easydict" not in sys.modules
+    assert isinstance(ckpt["config"], checkpoint.AttrDict) and ckpt["config"].model.hidden_dim == 128
+    assert ckpt["config"].model.smooth_conv is True and ckpt["config"].train.seed == 2021 and ckpt["iteration"] == 5000
+    import agdiff_b200
+    m2 = agdiff_b200.get_model(ckpt["config"].model)
+    m2.load_state_dict(ckpt["model"])
+    from util import checksum
+    assert checksum(state_dict_cpu(m2)) == checksum(state_dict_cpu(m))
+    cfg_path = tmp_path / "drugs.yml"
+    cfg_path.write_text("model:\n  network: dualenc\n  hidden_dim: 128\n  beta_start: 1.e-7\ntrain:\n  seed: 2021\n")
+    c = checkpoint.load_config(str(cfg_path))
+    assert c.model.network == "dualenc" and c.model.beta_start == 1e-7 and c.train.seed == 2021
