@@ -559,11 +559,73 @@ class DualEncoderEpsNetwork(nn.Module):
         finally:
             nb.close()
 
-    # ------------------------------------------------------------------ loss (out of scope)
-    def get_loss(self, *args, **kwargs):
-        raise NotImplementedError("training (get_loss / autograd) is outside the accelerated sampling path")
+    # ------------------------------------------------------------------ loss (forward value only)
+    def _eq_transform(self, score_d, pos, edge_index, edge_length):
+        """geometry.py:9-17 through the native op (agd_op_eq_transform): (E,1),(N,3),(2,E),(E,1) -> (N,3)"""
+        lib, dev = _lib.load(), self._device()
+        E, N = int(edge_index.size(1)), int(pos.size(0))
+        out = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        keep = [score_d.reshape(-1).to(dev, torch.float32).contiguous(), pos.to(dev, torch.float32).contiguous(),
+                _i32(edge_index[0].to(dev)), _i32(edge_index[1].to(dev)), edge_length.reshape(-1).to(dev, torch.float32).contiguous()]
+        _lib.check(lib.agd_op_eq_transform(*[_ptr(t) for t in keep], E, N, _ptr(out), self._stream()))
+        torch.cuda.current_stream(dev).synchronize()       # `keep` must outlive the launch
+        return out
 
-    get_loss_diffusion = get_loss
+    def get_loss(self, atom_type, pos, bond_index, bond_type, batch, num_nodes_per_graph, num_graphs, anneal_power=2.0,
+                 return_unreduced_loss=False, return_unreduced_edge_loss=False, extend_order=True, extend_radius=True, **kwargs):
+        """reference dualenc.py:253-282 (dispatcher)"""
+        return self.get_loss_diffusion(atom_type, pos, bond_index, bond_type, batch, num_nodes_per_graph, num_graphs, anneal_power,
+                                       return_unreduced_loss, return_unreduced_edge_loss, extend_order, extend_radius, **kwargs)
+
+    def get_loss_diffusion(self, atom_type, pos, bond_index, bond_type, batch, num_nodes_per_graph, num_graphs, anneal_power=2.0,
+                           return_unreduced_loss=False, return_unreduced_edge_loss=False, extend_order=True, extend_radius=True,
+                           **kwargs):
+        """FORWARD VALUE of the denoising loss, reference dualenc.py:284-395 (validation / monitoring): noise-level sampling,
+        position perturbation, the score network on the perturbed positions, four eq_transforms, per-atom loss.  The native
+        path has no autograd, so the result carries no graph - training stays with the reference.  Extensions: ``time_step=``
+        (G,) and ``pos_noise=`` (N,3) inject the two random draws (defaults draw them exactly like the reference does)."""
+        dev = self._device()
+        atom_type, pos, batch = atom_type.to(dev), pos.to(dev, torch.float32), batch.to(dev)
+        node2graph = batch
+        with torch.no_grad():
+            time_step = kwargs.get("time_step")
+            if time_step is None:
+                time_step = torch.randint(0, self.num_timesteps, size=(num_graphs // 2 + 1,), device=dev)
+                time_step = torch.cat([time_step, self.num_timesteps - time_step - 1], dim=0)[:num_graphs]
+            time_step = time_step.to(dev)
+            a = self.alphas.index_select(0, time_step)                       # (G,)
+            a_pos = a.index_select(0, node2graph).unsqueeze(-1)               # (N,1)
+            pos_noise = kwargs.get("pos_noise")
+            if pos_noise is None:
+                pos_noise = torch.zeros(size=pos.size(), device=dev)
+                pos_noise.normal_()
+            pos_noise = pos_noise.to(dev, torch.float32)
+            pos_perturbed = pos + pos_noise * (1.0 - a_pos).sqrt() / a_pos.sqrt()
+            (edge_inv_global, edge_inv_local, edge_index, edge_type, edge_length, local_edge_mask) = self(
+                atom_type=atom_type, pos=pos_perturbed, bond_index=bond_index, bond_type=bond_type, batch=batch,
+                time_step=time_step, return_edges=True, extend_order=extend_order, extend_radius=extend_radius)
+            edge2graph = node2graph.index_select(0, edge_index[0])
+            a_edge = a.index_select(0, edge2graph).unsqueeze(-1)              # (E,1)
+            d_gt = (pos[edge_index[0]] - pos[edge_index[1]]).norm(dim=-1).unsqueeze(-1)
+            d_perturbed = edge_length                                         # is_train_edge == all True, dualenc.py:570-572
+            d_target = (d_gt - d_perturbed) / (1.0 - a_edge).sqrt() * a_edge.sqrt()
+            lmask = local_edge_mask.unsqueeze(-1)
+            global_mask = torch.logical_and(torch.logical_or(d_perturbed <= self.config.cutoff, lmask), ~lmask)
+            target_d_global = torch.where(global_mask, d_target, torch.zeros_like(d_target))
+            edge_inv_global = torch.where(global_mask, edge_inv_global, torch.zeros_like(edge_inv_global))
+            target_pos_global = self._eq_transform(target_d_global, pos_perturbed, edge_index, edge_length)
+            node_eq_global = self._eq_transform(edge_inv_global, pos_perturbed, edge_index, edge_length)
+            loss_global = 2 * torch.sum((node_eq_global - target_pos_global) ** 2, dim=-1, keepdim=True)
+            ei_l, el_l = edge_index[:, local_edge_mask], edge_length[local_edge_mask]
+            target_pos_local = self._eq_transform(d_target[local_edge_mask], pos_perturbed, ei_l, el_l)
+            node_eq_local = self._eq_transform(edge_inv_local, pos_perturbed, ei_l, el_l)
+            loss_local = 5 * torch.sum((node_eq_local - target_pos_local) ** 2, dim=-1, keepdim=True)
+            loss = loss_global + loss_local
+        if return_unreduced_edge_loss:
+            return None                                                      # the reference's `pass`
+        if return_unreduced_loss:
+            return loss, loss_global, loss_local
+        return loss
 
     # ------------------------------------------------------------------ samplers
     def langevin_dynamics_sample(self, atom_type, pos_init, bond_index, bond_type, batch, num_graphs, extend_order,

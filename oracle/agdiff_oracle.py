@@ -328,6 +328,37 @@ def sample(sd, cfg, atom_type, pos_init, bond_index, bond_type, batch, num_graph
 
 
 # ----------------------------------------------------------------------------- helpers for tests
+def loss_draws(num_graphs, n_atoms, num_timesteps, rng_seed):
+    """the two random draws of get_loss_diffusion in the reference's order (dualenc.py:302-313), from the global CPU generator"""
+    torch.manual_seed(rng_seed)
+    ts = torch.randint(0, num_timesteps, size=(num_graphs // 2 + 1,))
+    ts = torch.cat([ts, num_timesteps - ts - 1], dim=0)[:num_graphs]
+    noise = torch.zeros(n_atoms, 3)
+    noise.normal_()
+    return ts, noise
+
+
+def loss_diffusion(sd, cfg, atom_type, pos, bond_index, bond_type, batch, num_graphs, time_step, pos_noise, extend_order=True,
+                   extend_radius=True):
+    """get_loss_diffusion dualenc.py:284-395 with the two random draws injected -> (loss, loss_global, loss_local), each (N, 1)."""
+    alphas = alphas_from_cfg(cfg).to(pos.dtype)
+    a = alphas.index_select(0, time_step)
+    a_pos = a.index_select(0, batch).unsqueeze(-1)
+    pos_p = pos + pos_noise.to(pos.dtype) * (1.0 - a_pos).sqrt() / a_pos.sqrt()
+    eg, el, ei, et, elen, lmask = forward(sd, cfg, atom_type, pos_p, bond_index, bond_type, batch, extend_order, extend_radius)
+    a_edge = a.index_select(0, batch.index_select(0, ei[0])).unsqueeze(-1)
+    d_gt = edge_lengths(pos, ei).unsqueeze(-1)
+    d_target = (d_gt - elen) / (1.0 - a_edge).sqrt() * a_edge.sqrt()          # is_train_edge == all True (:570-572)
+    lm = lmask.unsqueeze(-1)
+    gmask = torch.logical_and(torch.logical_or(elen <= cfg["cutoff"], lm), ~lm)
+    tgt_g = torch.where(gmask, d_target, torch.zeros_like(d_target))
+    eg = torch.where(gmask, eg, torch.zeros_like(eg))
+    loss_g = 2 * ((eq_transform(eg, pos_p, ei, elen) - eq_transform(tgt_g, pos_p, ei, elen)) ** 2).sum(-1, keepdim=True)
+    li, ll_len = ei[:, lmask], elen[lmask]
+    loss_l = 5 * ((eq_transform(el, pos_p, li, ll_len) - eq_transform(d_target[lmask], pos_p, li, ll_len)) ** 2).sum(-1, keepdim=True)
+    return loss_g + loss_l, loss_g, loss_l
+
+
 def perturb_state_dict(sd: Dict[str, torch.Tensor], seed: int = 7) -> Dict[str, torch.Tensor]:
     """Deterministically perturbs the constants that are trivial at init (BN running stats and
     affine, ShiftedSoftplus beta, GIN eps, zero biases) so that folded constants are exercised

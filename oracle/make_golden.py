@@ -143,6 +143,21 @@ def gen_traj(ref, name, cfg_name, kind, seed, n_steps, t_start, clip_local, gss,
     print(name, "steps", n_steps, "t_start", t_start, "|pos|max", float(pos.abs().max()))
 
 
+def gen_loss(ref, name, cfg_name, kind, seed, perturb, pos_seed, pos_scale, rng_seed):
+    """forward value of get_loss_diffusion (dualenc.py:284-395); its two random draws (noise levels, position noise) come from the
+    global CPU generator seeded with ``rng_seed`` - the test re-creates them with the same two calls in the same order"""
+    m = ref_model(ref, cfg_name, seed, perturb)
+    z, bi, bt, b, G, pos = case_inputs(kind, pos_seed, pos_scale)
+    csum = checksum(m.state_dict())
+    torch.manual_seed(rng_seed)
+    with torch.no_grad():
+        loss, lg, ll = m.get_loss(z, pos, bi, bt, b, None, G, return_unreduced_loss=True, extend_order=False)
+    torch.save(dict(cfg_name=cfg_name, kind=kind, seed=seed, perturb=perturb, pos_seed=pos_seed, pos_scale=pos_scale, checksum=csum,
+                    rng_seed=rng_seed, atom_type=z, bond_index=bi, bond_type=bt, batch=b, pos=pos, num_graphs=G,
+                    loss=loss, loss_global=lg, loss_local=ll), os.path.join(GOLDEN, name + ".pt"))
+    print(name, "N", z.numel(), "loss mean %.4e global %.4e local %.4e" % (float(loss.mean()), float(lg.mean()), float(ll.mean())))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = ref_shims.load_reference()
@@ -155,6 +170,8 @@ def main():
     gen_traj(ref, "traj_alanine2_high", "qm9", "alanine2", 2021, 100, 5000, 20.0, 0.5, 1.0, 1.0)
     gen_traj(ref, "traj_alanine2_low", "qm9", "alanine2", 2021, 100, 100, 20.0, 0.5, 1.0, 1.2)
     gen_traj(ref, "traj_qm9x6_low_smooth", "drugs", "qm9x6", 2021, 40, 1500, 20.0, 0.5, 1.0, 1.5)
+    gen_loss(ref, "loss_drugs_mixed_smooth", "drugs", "drugs_mixed", 2021, 9, 6, 1.5, 77)
+    gen_loss(ref, "loss_qm9x6", "qm9", "qm9x6", 2021, 0, 7, 1.2, 78)
 
 
 if __name__ == "__main__":

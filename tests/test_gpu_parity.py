@@ -606,3 +606,24 @@ def test_frontend_batched_equals_one_molecule_per_call():
     for t, a, mol in zip(traj, one_call, mols):
         assert t.pos_gen.shape == (3, 2 * mol.num_nodes, 3) and torch.equal(t.pos_gen[-1], a.pos_gen)
     assert m.range_fallbacks == 0
+
+
+@pytest.mark.parametrize("name", ["loss_drugs_mixed_smooth", "loss_qm9x6"])
+def test_loss_forward_value_matches_reference_golden(name):
+    """get_loss_diffusion (dualenc.py:284-395), forward value only: per-atom losses of the unmodified reference (golden) with its
+    two random draws re-created from the recorded seed and injected through the time_step= / pos_noise= extensions."""
+    g = golden(name)
+    m, sd = _cuda_model(g["cfg_name"], g["seed"], g["perturb"])
+    ts, noise = O.loss_draws(g["num_graphs"], g["atom_type"].numel(), 5000, g["rng_seed"])
+    loss, lg, ll = m.get_loss(g["atom_type"].to(DEV), g["pos"].to(DEV), g["bond_index"].to(DEV), g["bond_type"].to(DEV),
+                              g["batch"].to(DEV), None, g["num_graphs"], return_unreduced_loss=True, extend_order=False,
+                              time_step=ts, pos_noise=noise)
+    for a, b, what in ((loss, g["loss"], "loss"), (lg, g["loss_global"], "loss_global"), (ll, g["loss_local"], "loss_local")):
+        a = a.cpu()
+        assert a.shape == b.shape and not a.requires_grad
+        assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max()), "%s: %.3e vs max %.3e" % (
+            what, float((a - b).abs().max()), float(b.abs().max()))
+    # without injection the draws come from torch's generators like in the reference: finite, right shape
+    l2 = m.get_loss_diffusion(g["atom_type"].to(DEV), g["pos"].to(DEV), g["bond_index"].to(DEV), g["bond_type"].to(DEV),
+                              g["batch"].to(DEV), None, g["num_graphs"], extend_order=False)
+    assert l2.shape == g["loss"].shape and bool(torch.isfinite(l2).all())
