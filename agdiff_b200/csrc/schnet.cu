@@ -250,7 +250,8 @@ static int tiles_grid(int64_t rows_cap, int num_sms, int per_sm) {
 
 void launch_filters(const LaunchCtx& c, const BatchDev& b, const ModelW& mw, int blk) {
   if (c.use_tc == 2) {
-    launch_filters_f16(c, b, mw, blk);
+    if (c.f16_ws && c.f16_fuse) launch_filters_f16_ws(c, b, mw, blk);
+    else launch_filters_f16(c, b, mw, blk);
     return;
   }
   if (c.use_tc) {

@@ -34,30 +34,9 @@
 
 #include "kernels.h"
 #include "tc16_common.cuh"
+#include "tc_filter16.cuh"
 
 namespace agd {
-
-constexpr int LDS_W = 68;               // padded row stride (floats) of the 64-column filter half-tile awaiting aggregation
-
-struct TcF16Args {
-  const uint32_t* W1img;   // [hi | lo'] fp16 images of F1 (K=128): each (128/64) x F rows x 128 B
-  const uint32_t* W2img;   // ... of F2 (K=F)
-  const float *f1b, *f2b, *beta_ptr;
-  const float* cw;         // [E] envelope * distance weight of this conv (edge_weight_kernel)
-  const float* wsc;        // [0] = 1/scale(F1), [1] = 1/scale(F2)
-  const int* n_rows_dev;
-  const uint4* g2h;        // pre-split encoder state (tc_common.cuh: g2h_index)
-  float* filt;             // [E][192]  (!FUSE)
-  int col0;                // 0 (conv1) or 128 (conv2): column offset in filt / xcat / agg
-  int scaled;              // 1: lo' scaled by 2^S + scale-input-d, 0: unscaled lo (A/B switch AGD_F16_LOSHIFT=0)
-  int* range_flag;
-  int debug_filt;          // FUSE: also write the filter tensor (tests / diagnostics)
-  unsigned long long* timing;   // diagnostics: [group][observer 0/1][8 phases] accumulated cycles (nullptr: off)
-  // fused aggregation (FUSE): agg[dst][col0 + n] = sum over the destination's edges, in CSC order, of x[src][col0 + n] * W_e[n]
-  const float* xcat;       // [N][192]
-  float* agg;              // [N][192]; rows of atoms without in-edges are not written (tc_node_kernel treats them as zero)
-  const int *e_src, *e_dst, *in_ptr;
-};
 
 template <int F, bool FUSE>
 struct TcF16Smem {
@@ -66,15 +45,6 @@ struct TcF16Smem {
   static constexpr size_t bytes = 1024 + 2 * W1_HALF + 2 * W2_HALF + (128 + 128) * sizeof(float) + fuse_bytes +
                                   16 * sizeof(uint64_t) + 64;
 };
-
-// softplus(y) - ln2 with the argument already in log2 units (y2 = y * log2 e): ln2 * (log2(1 + 2^y2) - 1); the
-// linear branch of F.softplus' threshold (y > 20) keeps the MUFU chain from overflowing
-__device__ __forceinline__ float ssp_log2(float y2) {
-  float e, sp;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y2));
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(sp) : "f"(1.0f + e));
-  return fmaf((y2 > 28.853900817779268f) ? y2 : sp, LN2F, -LN2F);
-}
 
 // CFConv edge weight lw(d) * C(d) (schnet.py:90-100,140-147) with the distance MLP staged in shared memory [w1 | b1 | w2 | b2],
 // read as float4 (same arithmetic, in the same order, as cfconv_edge_weight_smem)
