@@ -1,5 +1,6 @@
-"""Error of the CUDA forward vs the fp32 reference (golden) and vs the fp64 oracle, for the tensor-core
-(3xTF32 tcgen05) and the fp32 FFMA kernel paths.  Evidence for DESIGN.md section 5; run on a GPU box."""
+"""TEST INFRASTRUCTURE (lives under tests/ because it uses the oracle as checker): error of the CUDA forward vs the fp32 reference
+(golden) and vs the fp64 oracle, for every arithmetic mode (fp16-split, 3xTF32, FFMA).  Evidence for DESIGN.md section 5 /
+profiles/r01_accuracy_tc_vs_ffma.md; run on a GPU box:  python tests/accuracy_report.py"""
 import os
 import subprocess
 import sys
@@ -8,7 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))   # util.py
 from oracle import agdiff_oracle as O
 from util import CONFIGS, golden, make_model, state_dict_cpu
 
