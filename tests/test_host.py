@@ -271,3 +271,41 @@ def test_reference_checkpoint_loads_without_easydict(tmp_path):
     cfg_path.write_text("model:\n  network: dualenc\n  hidden_dim: 128\n  beta_start: 1.e-7\ntrain:\n  seed: 2021\n")
     c = checkpoint.load_config(str(cfg_path))
     assert c.model.network == "dualenc" and c.model.beta_start == 1e-7 and c.train.seed == 2021
+
+
+@pytest.mark.parametrize("ascale", [1.0, 1.0e-3, 3.0e3])
+def test_fp16_split_arithmetic_model(ascale):
+    """Numerical model of the "3xFP16" scheme of csrc/tc16_common.cuh, emulated in numpy (products exact, fp64 accumulation):
+    x = hi + lo' * 2^-11 with fp16 parts, D = (sum a_hi.w_lo' + a_lo'.w_hi) * 2^-11 + sum a_hi.w_hi reproduces the fp32 product to
+    ~2^-22 at ANY activation magnitude inside the fp16 range (the 2^11 pre-scale keeps the lo parts normal), whereas unscaled lo
+    parts lose precision once they go subnormal - which is why the cross terms are folded with scale-input-d."""
+    rng = np.random.default_rng(5)
+    M, K, N, S = 256, 128, 64, 11
+    a = (rng.standard_normal((M, K)) * ascale).astype(np.float32)
+    w = rng.uniform(-0.15, 0.15, (N, K)).astype(np.float32)
+    ref = a.astype(np.float64) @ w.astype(np.float64).T
+    img, inv = pack.umma_image_f16(w, S)
+    e = int(round(-np.log2(inv)))
+    ws = np.ldexp(w, e).astype(np.float32)
+    w_hi = ws.astype(np.float16).astype(np.float64)
+    w_lo = np.ldexp(ws - w_hi.astype(np.float32), S).astype(np.float16).astype(np.float64)
+
+    def split(x, shift):
+        hi = x.astype(np.float16).astype(np.float32)
+        lo = np.ldexp(x - hi, shift).astype(np.float16)
+        return hi.astype(np.float64), lo.astype(np.float64)
+
+    a_hi, a_lo = split(a, S)
+    cross = a_hi @ w_lo.T + a_lo @ w_hi.T
+    d = (cross * 2.0 ** -S + a_hi @ w_hi.T) * inv
+    err = float(np.abs(d - ref).max() / np.abs(ref).max())
+    assert err < 3e-7, err                                     # fp32 FFMA itself: ~4e-7 on this problem
+    # A/B: unscaled lo parts of the ACTIVATION (weights keep their power-of-two pre-scale)
+    a_hi0, a_lo0 = split(a, 0)
+    w_lo0 = (ws - w_hi.astype(np.float32)).astype(np.float16).astype(np.float64)
+    d0 = (a_hi0 @ w_lo0.T + a_lo0 @ w_hi.T + a_hi0 @ w_hi.T) * inv
+    err0 = float(np.abs(d0 - ref).max() / np.abs(ref).max())
+    if ascale < 0.01:
+        assert err0 > 10 * err                                 # subnormal lo parts: visibly worse
+    else:
+        assert err0 < 1e-6
