@@ -1,5 +1,7 @@
-// EXPERIMENTAL (opt-in: agd_set_option "f16_ws" / env AGD_F16_WS=1; written at the end of round 1 WITHOUT GPU time left to run
-// it - it compiles, it has not executed yet; the default CFConv kernel is tc_filter16.cu).
+// EXPERIMENTAL (opt-in: agd_set_option "f16_ws" / env AGD_F16_WS=1; the default CFConv kernel is tc_filter16.cu).  Written at the
+// end of round 1 with the last GPU seconds of the round: FUNCTIONALLY validated - with AGD_F16_WS=1 the bit-for-bit tests against the
+// stand-alone aggregate kernel pass (test_f16_fused_aggregation_bitwise_equals_unfused x3, test_supplied_complete_graph_long_runs) -
+// but NOT yet timed or profiled, hence not the default.
 //
 // Warp-specialised CFConv kernel of the fp16-split family.  Same math, same tiles, same summation order as
 // tc_filter16_kernel<F, fused> - only the division of labour changes.  There, each 8-warp group owns a tile end to end, so the

@@ -204,7 +204,7 @@ int agd_get_mode(const agd_handle* h);
  *   "f16_pair"  (env AGD_F16_PAIR)  pair MLPs on the fp16 two-slot kernels
  *   "f16_node"  (env AGD_F16_NODE)  SchNet node chain on the fp16 kernel with double-buffered weight streaming
  *   "f16_ws"    (env AGD_F16_WS, default 0)  EXPERIMENTAL warp-specialised CFConv kernel (tc_filter16_ws.cu: epilogue warps /
- *               aggregation warps); compiles, not yet validated on hardware - do not enable in production
+ *               aggregation warps); passes the bit-for-bit aggregation tests, not yet timed - hence off
  *   "f16_debug_filt" (0)  the fused CFConv kernels also write the filter tensor (tests)
  *   "f16_timing"     (0)  clock64 phase counters of the CFConv kernels (needs a build with -DAGD_F16_TIMING), agd_debug_timing */
 int agd_set_option(agd_handle* h, const char* name, int value);
