@@ -319,6 +319,8 @@ def run_ours(args):
             variants = [
                 ("schnet.cfconv128_f16", "tc_filter16_kernel<128, fused> (CFConv filter net + aggregation, tcgen05 kind::f16, fp16 hi/lo' split, "
                                          "two edge tiles in flight per SM)", 3, "3 fp16 MMAs per product at the bf16 rate"),
+                ("schnet.cfconv128_f16ws", "tc_filter16_ws_kernel<128> (warp-specialised CFConv filter net + aggregation, tcgen05 kind::f16, "
+                                           "fp16 hi/lo' split; opt-in AGD_F16_WS=1)", 3, "3 fp16 MMAs per product at the bf16 rate"),
                 ("schnet.filter128_f16", "tc_filter16_kernel<128> (CFConv filter net, tcgen05 kind::f16, fp16 hi/lo' split)", 3,
                  "3 fp16 MMAs per product at the bf16 rate"),
                 ("schnet.filter128_tc", "tc_filter_kernel<128> (CFConv filter net, tcgen05 kind::tf32, 3xTF32 split)", 6,
@@ -341,7 +343,7 @@ def run_ours(args):
                     roof["achieved_tensor_tflops_issued"] = round(mult / (2 if mult == 6 else 1) * ach, 3)
                     roof["attainable_peak"] = round(peak / mult, 1)
                     roof["frac_of_attainable"] = round(ach / (peak / mult), 4)
-                if label == "schnet.cfconv128_f16":
+                if label in ("schnet.cfconv128_f16", "schnet.cfconv128_f16ws"):
                     # HBM side of the same launch: the pre-split g2 tile stream in (512 B / edge) + agg rows out; x gathers are L2 hits
                     byts = E * 512 + int(z.numel()) * 512
                     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
