@@ -21,7 +21,7 @@ void set_tc_node_attributes();
 void set_tc16_attributes();
 void set_tc_mlp16_attributes();
 void set_tc_node16_attributes();
-void set_tc16_ws_attributes();
+void set_tc_cfconv_attributes();
 }  // namespace agd
 
 using namespace agd;
@@ -58,7 +58,6 @@ struct agd_handle {
   int f16_mlp = 1;
   int f16_pair = 1;
   int f16_node = 1;
-  int f16_ws = 0;
   int f16_debug_filt = 0;
   unsigned long long* f16_timing = nullptr;
   int use_tc = 2;   // AGD_TC_FILTERS / agd_set_mode: 0 FFMA, 1 tcgen05 3xTF32, 2 tcgen05 + 3xFP16 filter kernels
@@ -150,7 +149,6 @@ static LaunchCtx make_ctx(agd_handle* h) {
   c.f16_mlp = (h->use_tc == 2) ? h->f16_mlp : 0;
   c.f16_pair = (h->use_tc == 2) ? h->f16_pair : 0;
   c.f16_node = (h->use_tc == 2) ? h->f16_node : 0;
-  c.f16_ws = (h->use_tc == 2) ? h->f16_ws : 0;
   c.f16_debug_filt = h->f16_debug_filt;
   c.f16_timing = h->f16_timing;
   c.cutoff = h->cfg.cutoff;
@@ -248,12 +246,11 @@ int agd_create(const agd_config* cfg, agd_handle** out) {
   set_tc16_attributes();
   set_tc_mlp16_attributes();
   set_tc_node16_attributes();
-  set_tc16_ws_attributes();
+  set_tc_cfconv_attributes();
   h->f16_fuse = f16_fuse_default();
   if (const char* e = std::getenv("AGD_F16_MLP")) h->f16_mlp = (e[0] != '0');
   if (const char* e = std::getenv("AGD_F16_PAIR")) h->f16_pair = (e[0] != '0');
   if (const char* e = std::getenv("AGD_F16_NODE")) h->f16_node = (e[0] != '0');
-  if (const char* e = std::getenv("AGD_F16_WS")) h->f16_ws = (e[0] != '0');
   if (const char* e = std::getenv("AGD_TC_FILTERS")) h->use_tc = (e[0] == '0') ? 0 : (e[0] == '1') ? 1 : 2;
   CUDA_TRY(cudaGetLastError());
   *out = h;
@@ -638,7 +635,6 @@ int agd_op_cfconv_aggregate(const float* x, const float* W, const int32_t* src, 
   c.f16_mlp = 0;
   c.f16_pair = 0;
   c.f16_node = 0;
-  c.f16_ws = 0;
   c.f16_debug_filt = 0;
   c.f16_timing = nullptr;
   launch_aggregate(c, x, W, src, in_ptr, n_nodes, F, out);
@@ -693,7 +689,6 @@ int agd_set_option(agd_handle* h, const char* name, int value) {
   else if (std::strcmp(name, "f16_mlp") == 0) h->f16_mlp = value ? 1 : 0;
   else if (std::strcmp(name, "f16_pair") == 0) h->f16_pair = value ? 1 : 0;
   else if (std::strcmp(name, "f16_node") == 0) h->f16_node = value ? 1 : 0;
-  else if (std::strcmp(name, "f16_ws") == 0) h->f16_ws = value ? 1 : 0;
   else if (std::strcmp(name, "f16_debug_filt") == 0) h->f16_debug_filt = value ? 1 : 0;
   else if (std::strcmp(name, "f16_timing") == 0) {   // diagnostics: 1 = allocate + zero the phase counters, 0 = off
     if (value && !h->f16_timing) {

@@ -128,8 +128,7 @@ struct LaunchCtx {
   int f16_mlp;     // use_tc == 2: edge encoder on the fp16 two-slot kernels (tc_mlp16.cu)
   int f16_pair;    // use_tc == 2: pair MLPs on the fp16 two-slot kernels
   int f16_node;    // use_tc == 2: SchNet node chain on the fp16 kernel with double-buffered weight streaming (tc_node16.cu)
-  int f16_ws;      // use_tc == 2: EXPERIMENTAL warp-specialised CFConv kernel (tc_filter16_ws.cu), default 0
-  int f16_fuse;    // use_tc == 2: CFConv aggregation fused into the filter kernels (no filt tensor, no aggregate kernel)
+  int f16_fuse;    // use_tc == 2: both CFConv layers of a block + the aggregation in one launch (tc_cfconv.cu; no filt tensor, no aggregate kernel)
   float cutoff;
   int smooth;
   int num_convs, num_convs_local;
@@ -150,7 +149,7 @@ void launch_pair_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w, c
 void launch_filters(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);
 void launch_filters_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);   // tc_filter.cu
 void launch_edge_weights_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& w);   // tc_filter16.cu, once per evaluation
-void launch_filters_f16_ws(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);   // tc_filter16_ws.cu (experimental)
+void launch_cfconv_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);   // tc_cfconv.cu: conv1 + conv2 + aggregation
 void launch_filters_f16(const LaunchCtx& c, const BatchDev& b, const ModelW& w, int blk);  // tc_filter16.cu
 int f16_lo_shift();   // S of the fp16 lo' = (x - hi) * 2^S split (0: unscaled), pack.py must build the weight images with it
 int f16_fuse_default();    // AGD_F16_FUSE (default 1): launch_filters_f16 also performs the CFConv aggregation into agg

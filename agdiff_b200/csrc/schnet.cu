@@ -57,6 +57,11 @@ __global__ void __launch_bounds__(NT, 2) filter_kernel(const FiltArgs a) {
 // its in-edges are read as one contiguous stream and the source rows as F*4-byte gathers (L2 hits:
 // a molecule's x fits in a few KB).  HBM-bound: algorithmic bytes per edge = 4F (filter) + 4F (gather)
 // + 4 (index), per atom 4F (write) + 4 (pointer).
+// SUMMATION ORDER (the definition every CFConv aggregation in this library follows, tc_cfconv.cu included, so that they agree
+// bit for bit): the in-edges of a destination, in CSC order, are dealt round-robin to FOUR partial sums by their position in
+// the run (edge e0 + p goes to partial p mod 4), each partial accumulates its edges in order with one fmaf per edge, and the
+// result is (s0 + s1) + (s2 + s3).  The position in the run does not depend on tile, CTA or batch boundaries, so neither does
+// the result; four independent chains also give the gather four times the memory-level parallelism of one.
 template <int F>
 __global__ void __launch_bounds__(F) cfconv_aggregate_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                              const int* __restrict__ src, const int* __restrict__ in_ptr,
@@ -67,36 +72,37 @@ __global__ void __launch_bounds__(F) cfconv_aggregate_kernel(const float* __rest
   const int c4 = threadIdx.x % TPN;
   if (node >= n_nodes) return;
   const int e0 = in_ptr[node], e1 = in_ptr[node + 1];
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  int e = e0;
-  for (; e + 4 <= e1; e += 4) {
+  float4 acc[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e = e0; e < e1; e += 4) {
     int s[4];
     float4 wv[4], xv[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) s[u] = __ldg(src + e + u);
+    for (int u = 0; u < 4; ++u) s[u] = (e + u < e1) ? __ldg(src + e + u) : 0;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      wv[u] = __ldcs(reinterpret_cast<const float4*>(W + (size_t)(e + u) * F) + c4);
-      xv[u] = __ldg(reinterpret_cast<const float4*>(x + (size_t)s[u] * F) + c4);
+      if (e + u < e1) {
+        wv[u] = __ldcs(reinterpret_cast<const float4*>(W + (size_t)(e + u) * F) + c4);
+        xv[u] = __ldg(reinterpret_cast<const float4*>(x + (size_t)s[u] * F) + c4);
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      acc.x = fmaf(xv[u].x, wv[u].x, acc.x);
-      acc.y = fmaf(xv[u].y, wv[u].y, acc.y);
-      acc.z = fmaf(xv[u].z, wv[u].z, acc.z);
-      acc.w = fmaf(xv[u].w, wv[u].w, acc.w);
+      if (e + u < e1) {
+        acc[u].x = fmaf(xv[u].x, wv[u].x, acc[u].x);
+        acc[u].y = fmaf(xv[u].y, wv[u].y, acc[u].y);
+        acc[u].z = fmaf(xv[u].z, wv[u].z, acc[u].z);
+        acc[u].w = fmaf(xv[u].w, wv[u].w, acc[u].w);
+      }
     }
   }
-  for (; e < e1; ++e) {
-    const int s = __ldg(src + e);
-    const float4 wv = __ldcs(reinterpret_cast<const float4*>(W + (size_t)e * F) + c4);
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)s * F) + c4);
-    acc.x = fmaf(xv.x, wv.x, acc.x);
-    acc.y = fmaf(xv.y, wv.y, acc.y);
-    acc.z = fmaf(xv.z, wv.z, acc.z);
-    acc.w = fmaf(xv.w, wv.w, acc.w);
-  }
-  reinterpret_cast<float4*>(out + (size_t)node * F)[c4] = acc;
+  float4 r;
+  r.x = (acc[0].x + acc[1].x) + (acc[2].x + acc[3].x);
+  r.y = (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y);
+  r.z = (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z);
+  r.w = (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w);
+  reinterpret_cast<float4*>(out + (size_t)node * F)[c4] = r;
 }
 
 // ------------------------------------------------------------------ node-side kernel
@@ -250,7 +256,7 @@ static int tiles_grid(int64_t rows_cap, int num_sms, int per_sm) {
 
 void launch_filters(const LaunchCtx& c, const BatchDev& b, const ModelW& mw, int blk) {
   if (c.use_tc == 2) {
-    if (c.f16_ws && c.f16_fuse) launch_filters_f16_ws(c, b, mw, blk);
+    if (c.f16_fuse) launch_cfconv_f16(c, b, mw, blk);
     else launch_filters_f16(c, b, mw, blk);
     return;
   }

@@ -1,5 +1,5 @@
-// Arguments and small helpers shared by the two CFConv kernels of the fp16-split family: tc_filter16.cu (two groups, each
-// owning a tile end to end - the default) and tc_filter16_ws.cu (warp-specialised variant: epilogue warps / aggregation warps).
+// Arguments and small helpers shared by the CFConv kernels of the fp16-split family: tc_filter16.cu (one launch per conv, two
+// groups each owning a tile end to end; A/B and unfused path) and tc_cfconv.cu (both convs in one warp-specialised launch - the default).
 #pragma once
 #include "tc16_common.cuh"
 
@@ -7,7 +7,7 @@ namespace agd {
 
 constexpr int LDS_W = 68;               // padded row stride (floats) of the 64-column filter half-tile awaiting aggregation
 
-struct TcF16Args {
+struct TcF16Args {        // tc_filter16_kernel (unfused path)
   const uint32_t* W1img;   // [hi | lo'] fp16 images of F1 (K=128): each (128/64) x F rows x 128 B
   const uint32_t* W2img;   // ... of F2 (K=F)
   const float *f1b, *f2b, *beta_ptr;
@@ -15,16 +15,10 @@ struct TcF16Args {
   const float* wsc;        // [0] = 1/scale(F1), [1] = 1/scale(F2)
   const int* n_rows_dev;
   const uint4* g2h;        // pre-split encoder state (tc_common.cuh: g2h_index)
-  float* filt;             // [E][192]  (!FUSE)
-  int col0;                // 0 (conv1) or 128 (conv2): column offset in filt / xcat / agg
+  float* filt;             // [E][192]
+  int col0;                // 0 (conv1) or 128 (conv2): column offset in filt
   int scaled;              // 1: lo' scaled by 2^S + scale-input-d, 0: unscaled lo (A/B switch AGD_F16_LOSHIFT=0)
   int* range_flag;
-  int debug_filt;          // FUSE: also write the filter tensor (tests / diagnostics)
-  unsigned long long* timing;   // diagnostics: [group][observer 0/1][8 phases] accumulated cycles (nullptr: off)
-  // fused aggregation (FUSE): agg[dst][col0 + n] = sum over the destination's edges, in CSC order, of x[src][col0 + n] * W_e[n]
-  const float* xcat;       // [N][192]
-  float* agg;              // [N][192]; rows of atoms without in-edges are not written (tc_node_kernel treats them as zero)
-  const int *e_src, *e_dst, *in_ptr;
 };
 
 // softplus(y) - ln2 with the argument already in log2 units (y2 = y * log2 e): ln2 * (log2(1 + 2^y2) - 1); the

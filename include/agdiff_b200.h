@@ -198,13 +198,13 @@ enum { AGD_MODE_FFMA = 0, AGD_MODE_TF32 = 1, AGD_MODE_F16 = 2 };
 int agd_set_mode(agd_handle* h, int mode);
 int agd_get_mode(const agd_handle* h);
 /* tuning / A-B switches (AGD_MODE_F16 only; all default to 1 except the diagnostics):
- *   "f16_fuse"  (env AGD_F16_FUSE)  the CFConv aggregation runs inside the filter kernels (same sums in the same order as the
- *               stand-alone aggregate kernel, bit for bit); 0: filter tensor to HBM + aggregate kernel
+ *   "f16_fuse"  (env AGD_F16_FUSE)  both CFConv layers of a block (conv1 F=128, conv2 F=64) and the aggregation run in ONE
+ *               warp-specialised launch (tc_cfconv.cu: epilogue / aggregation / loader / MMA-issue warps, the encoder state is read
+ *               once per block; same sums in the same order as the stand-alone aggregate kernel, bit for bit);
+ *               0: one filter kernel per conv, filter tensor to HBM + aggregate kernel
  *   "f16_mlp"   (env AGD_F16_MLP)   edge encoder on the fp16 two-slot kernels (0: 3xTF32 kernels)
  *   "f16_pair"  (env AGD_F16_PAIR)  pair MLPs on the fp16 two-slot kernels
  *   "f16_node"  (env AGD_F16_NODE)  SchNet node chain on the fp16 kernel with double-buffered weight streaming
- *   "f16_ws"    (env AGD_F16_WS, default 0)  EXPERIMENTAL warp-specialised CFConv kernel (tc_filter16_ws.cu: epilogue warps /
- *               aggregation warps); passes the bit-for-bit aggregation tests, not yet timed - hence off
  *   "f16_debug_filt" (0)  the fused CFConv kernels also write the filter tensor (tests)
  *   "f16_timing"     (0)  clock64 phase counters of the CFConv kernels (needs a build with -DAGD_F16_TIMING), agd_debug_timing */
 int agd_set_option(agd_handle* h, const char* name, int value);
