@@ -251,6 +251,7 @@ int agd_create(const agd_config* cfg, agd_handle** out) {
   if (const char* e = std::getenv("AGD_F16_MLP")) h->f16_mlp = (e[0] != '0');
   if (const char* e = std::getenv("AGD_F16_PAIR")) h->f16_pair = (e[0] != '0');
   if (const char* e = std::getenv("AGD_F16_NODE")) h->f16_node = (e[0] != '0');
+  if (const char* e = std::getenv("AGD_F16_DEBUG")) h->f16_debug_filt = std::atoi(e);
   if (const char* e = std::getenv("AGD_TC_FILTERS")) h->use_tc = (e[0] == '0') ? 0 : (e[0] == '1') ? 1 : 2;
   CUDA_TRY(cudaGetLastError());
   *out = h;
@@ -689,7 +690,7 @@ int agd_set_option(agd_handle* h, const char* name, int value) {
   else if (std::strcmp(name, "f16_mlp") == 0) h->f16_mlp = value ? 1 : 0;
   else if (std::strcmp(name, "f16_pair") == 0) h->f16_pair = value ? 1 : 0;
   else if (std::strcmp(name, "f16_node") == 0) h->f16_node = value ? 1 : 0;
-  else if (std::strcmp(name, "f16_debug_filt") == 0) h->f16_debug_filt = value ? 1 : 0;
+  else if (std::strcmp(name, "f16_debug_filt") == 0) h->f16_debug_filt = value;   // bit 0: write filt; bits 1.. : timing experiments (tc_cfconv.cu)
   else if (std::strcmp(name, "f16_timing") == 0) {   // diagnostics: 1 = allocate + zero the phase counters, 0 = off
     if (value && !h->f16_timing) {
       if (cudaMalloc(&h->f16_timing, 64 * sizeof(unsigned long long)) != cudaSuccess) return fail(AGD_ERR_CUDA, "cudaMalloc");

@@ -21,13 +21,15 @@ struct TcF16Args {        // tc_filter16_kernel (unfused path)
   int* range_flag;
 };
 
-// softplus(y) - ln2 with the argument already in log2 units (y2 = y * log2 e): ln2 * (log2(1 + 2^y2) - 1); the
-// linear branch of F.softplus' threshold (y > 20) keeps the MUFU chain from overflowing
+// softplus(y) - ln2 with the argument already in log2 units (y2 = y * log2 e): ln2 * (log2(1 + 2^y2) - 1).  No threshold
+// branch (F.softplus switches to the identity above 20): for 24 < y2 < 128 the sum 1 + 2^y2 rounds to 2^y2 and lg2 returns y2
+// itself (abs. error ~2e-7), exactly what the linear branch yields; beyond 2^128 the chain gives +inf, which the fp16 split
+// turns into the range flag and the host into a re-run on the 3xTF32 kernels (ssp_fast there keeps the threshold).
 __device__ __forceinline__ float ssp_log2(float y2) {
   float e, sp;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y2));
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(sp) : "f"(1.0f + e));
-  return fmaf((y2 > 28.853900817779268f) ? y2 : sp, LN2F, -LN2F);
+  return fmaf(sp, LN2F, -LN2F);
 }
 
 }  // namespace agd
