@@ -49,10 +49,11 @@ using namespace tc;
 constexpr int CF_THREADS = 896;                    // 28 warps x 72 registers (27 used)
 constexpr int CF_WARP_D = 8, CF_WARP_L = 12, CF_WARP_R = 16, CF_WARP_M = 26;
 constexpr int CF_RWARPS = 5;                       // reducer warps per team; team 0 takes the even 32-column passes, team 1 the odd ones
+constexpr int CF_BKS = 3 * TM + 4;                    // ints of bookkeeping per tile parity: x-row offsets [128] | destinations [128] | run starts [128 + 1] (+ pad)
 constexpr int LDS_Q = 36;                          // padded row stride (floats) of a 32-column staging buffer
 constexpr uint32_t CFC_A1HI = 0, CFC_A1LO = 64, CFC_X1 = 128, CFC_Y1 = 256, CFC_X2 = 320, CFC_Y2 = 448;
 constexpr uint32_t CF_W1X = 2u * 128u * 128u * 2u, CF_W1Y = 2u * 128u * 64u * 2u, CF_W2X = 2u * 128u * 128u * 2u, CF_W2Y = 2u * 64u * 64u * 2u;
-constexpr int CF_STEPS = 12;                       // rows in flight per quarter-warp: 4 x 12 = 48 rows cover 99 % of the runs of a drug-like radius graph (in-degree = 32..33 radius neighbours + the local edges outside that set) in one round trip
+constexpr int CF_STEPS = 10;                       // rows in flight per quarter-warp: 4 x 10 = 40 rows cover 95 % of the runs of a drug-like radius graph (in-degree = 32..33 radius neighbours + the local edges outside that set) in one round trip
 enum { B_W = 0, B_A1_FULL, B_A1_FREE, B_D1X, B_D1Y, B_A2X, B_A2Y, B_D2X, B_D2Y, B_X2_FREE, B_Y2_FREE, B_FULL0, B_FULL1, B_EMPTY0, B_EMPTY1,
        B_BK_FULL0, B_BK_FULL1, B_BK_FREE0, B_BK_FREE1, B_COUNT };
 
@@ -76,7 +77,38 @@ struct CfArgs {
 };
 
 constexpr size_t CF_SMEM = 1024 + CF_W1X + CF_W1Y + CF_W2X + CF_W2Y + (128 + 64 + 128 + 64) * sizeof(float) +
-                           2 * TM * LDS_Q * sizeof(float) + 2 * 4 * 192 * sizeof(float) + (6 * TM + 8) * sizeof(int) + 24 * sizeof(uint64_t) + 64;
+                           2 * TM * LDS_Q * sizeof(float) + 2 * 4 * 192 * sizeof(float) + (2 * CF_BKS + 8) * sizeof(int) + 24 * sizeof(uint64_t) + 64;
+
+// ---- shared-memory layout as offsets from the 1024-byte-aligned base.  Every role recomputes the base (a few instructions)
+// instead of inheriting pointers from the kernel prologue: values that live across all role branches are what ptxas spills
+// first, and with ~4 KB of L1 left a spilled pointer costs an L2 round trip in front of every barrier wait.
+constexpr uint32_t CFO_B1X = CF_W1X + CF_W1Y + CF_W2X + CF_W2Y, CFO_B1Y = CFO_B1X + 128 * 4, CFO_B2X = CFO_B1Y + 64 * 4,
+                   CFO_B2Y = CFO_B2X + 128 * 4, CFO_W = CFO_B2Y + 64 * 4, CFO_CARRY = CFO_W + 2 * TM * LDS_Q * 4,
+                   CFO_BK = CFO_CARRY + 2 * 4 * 192 * 4, CFO_META = CFO_BK + 2 * CF_BKS * 4, CFO_BARS = CFO_META + 8 * 4;
+__device__ __forceinline__ uint32_t cf_sbase() {
+  extern __shared__ uint8_t smem_raw[];
+  uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  asm volatile("" : "+r"(sb));   // opaque: not merged with (and kept alive from) another role's copy
+  return sb;
+}
+__device__ __forceinline__ uint8_t* cf_generic(uint32_t saddr) { return static_cast<uint8_t*>(__cvta_shared_to_generic(saddr)); }
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_commit_s(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
 
 // ---- MMA issue: one elected lane of the (converged) MMA warp runs a whole layer; the other lanes skip it
 __device__ __forceinline__ bool elect_one() {
@@ -127,7 +159,7 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 // moved into uniform registers per instruction.  INPLACE: the operand was written over the accumulator in 16-column chunks
 // (epilogue 1): 16 fp32 columns = the 16 k values of one k-block become 8 hi words at a + 16 kb and 8 lo' words right behind.
 template <int K, int N, bool INPLACE, uint32_t D, uint32_t A_HI, uint32_t A_LO>
-__device__ __forceinline__ void cf_issue(uint64_t d_hi, bool scaled, uint64_t* bar0, uint64_t* bar1 = nullptr, uint64_t* bar2 = nullptr) {
+__device__ __forceinline__ void cf_issue(uint64_t d_hi, bool scaled, uint32_t bar0, uint32_t bar1 = 0u, uint32_t bar2 = 0u) {
   constexpr uint32_t idesc = idesc_f16(N);
   constexpr uint32_t half_bytes = static_cast<uint32_t>(K) * N * 2u;
   const uint64_t d_lo = d_hi + (half_bytes >> 4);
@@ -148,9 +180,9 @@ __device__ __forceinline__ void cf_issue(uint64_t d_hi, bool scaled, uint64_t* b
     mma_f16_ts(D, CF_HI_AT(kb), d_hi + boff16, idesc, 1u);
   }
   // tcgen05.commit: the barriers complete once every MMA issued so far has
-  mma_commit(bar0);
-  if (bar1) mma_commit(bar1);
-  if (bar2) mma_commit(bar2);
+  mma_commit_s(bar0);
+  if (bar1) mma_commit_s(bar1);
+  if (bar2) mma_commit_s(bar2);
   }
   __syncwarp();
 #undef CF_HI_AT
@@ -183,7 +215,7 @@ __device__ __forceinline__ void cf_epi1_chunk(uint32_t taddr, const float* s_b, 
 // One aggregation item: a destination run of the tile seen by one lane.  The quarter-warp rq (= lane / 8) owns the rows whose
 // position in the run is rq mod 4 - first, first + 4, ... < e - and the lane four columns of them.
 struct CfItem {
-  int s, first, e, dst_off;   // s: first row of the run in the tile; dst_off: agg row offset of the run's destination
+  int first, e, dst_off;   // dst_off: agg row offset of the run's destination
   bool cin, cout;          // the run continues from the previous tile / into the next one
 };
 
@@ -243,7 +275,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
   float* s_W = s_b2y + 64;                                 // [2][128][LDS_Q] ring of 32-column filter slabs awaiting aggregation
   float* s_carry = s_W + 2 * TM * LDS_Q;                   // [2 tile parities][4][192] partial sums of the run cut by a tile boundary (written in tile j, read in tile j + 1)
   int* s_bk = reinterpret_cast<int*>(s_carry + 2 * 4 * 192);   // [2 tile parities][3][128] x-row offsets (src * 192) | destinations | run starts
-  int* s_meta = s_bk + 2 * 3 * TM;                         // [2][4] runs in the tile, carry in, carry out, tile row where run 0 began
+  int* s_meta = s_bk + 2 * CF_BKS;                         // [2][4] runs in the tile, carry in, carry out, tile row where run 0 began
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_meta + 8);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 24);
 
@@ -312,6 +344,9 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
   if (warp < CF_WARP_D) {
     reg_dec<56>();
     // ================================================================== E: epilogue 1 of conv1, then of conv2, in place
+    const uint32_t sb = cf_sbase(), bar0 = sb + CFO_BARS;
+    const float* s_b1x = reinterpret_cast<const float*>(cf_generic(sb + CFO_B1X));
+    const float* s_b1y = s_b1x + 128;
     const int quad = warp & 3, half = warp >> 2;
     const uint32_t trow = static_cast<uint32_t>(quad * 32) << 16;
     const float inv1x = __ldg(a.wsc + 0) * (__ldg(a.beta_x) * 1.4426950408889634f);
@@ -322,7 +357,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
     pc.start(a.timing != nullptr && tid == 0);
     for (int j = 0; j < T; ++j) {
       const uint32_t ph = static_cast<uint32_t>(j) & 1u;
-      mbar_wait(&bars[B_D1X], ph);
+      mbar_wait_s(bar0 + 8 * B_D1X, ph);
       fence_after_sync();
       pc.tick(0);
 #pragma unroll
@@ -332,9 +367,9 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
       }
       wait_st();
       fence_before_sync();
-      mbar_arrive(&bars[B_A2X]);
+      mbar_arrive_s(bar0 + 8 * B_A2X);
       pc.tick(1);
-      mbar_wait(&bars[B_D1Y], ph);
+      mbar_wait_s(bar0 + 8 * B_D1Y, ph);
       fence_after_sync();
       pc.tick(2);
 #pragma unroll
@@ -344,7 +379,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
       }
       wait_st();
       fence_before_sync();
-      mbar_arrive(&bars[B_A2Y]);
+      mbar_arrive_s(bar0 + 8 * B_A2Y);
       pc.tick(3);
     }
     pc.flush(a.timing, 0);
@@ -352,6 +387,10 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
   } else if (warp < CF_WARP_L) {
     reg_dec<48>();
     // ================================================================== D: drain of layer 2 -> staging ring
+    const uint32_t sb = cf_sbase(), bar0 = sb + CFO_BARS;
+    const float* s_b2x = reinterpret_cast<const float*>(cf_generic(sb + CFO_B2X));
+    const float* s_b2y = s_b2x + 128;
+    float* s_W = reinterpret_cast<float*>(cf_generic(sb + CFO_W));
     const int quad = warp & 3;
     const int my_row = quad * 32 + lane;
     const uint32_t trow = static_cast<uint32_t>(quad * 32) << 16;
@@ -377,10 +416,10 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
         const bool isy = pass >= 4;
         const int n0 = isy ? (pass - 4) * 32 : pass * 32;
         const uint32_t b = n_pass & 1u, use = n_pass >> 1;
-        if (use > 0) mbar_wait(&bars[B_EMPTY0 + b], (use - 1) & 1u);   // the reducers are done with this slab's previous content
+        if (use > 0) mbar_wait_s(bar0 + 8 * (B_EMPTY0 + b), (use - 1) & 1u);   // the reducers are done with this slab's previous content
         pc.tick(1);
-        if (pass == 0) mbar_wait(&bars[B_D2X], ph);
-        if (pass == 4) mbar_wait(&bars[B_D2Y], ph);
+        if (pass == 0) mbar_wait_s(bar0 + 8 * B_D2X, ph);
+        if (pass == 4) mbar_wait_s(bar0 + 8 * B_D2Y, ph);
         fence_after_sync();
         pc.tick(2);
         const float inv2 = isy ? inv2y : inv2x, cw = isy ? cwy : cwx;
@@ -390,14 +429,14 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
         for (int cc = 0; cc < 2; ++cc) {
           uint32_t v[16];
           if (a.debug_filt & 8) {
-            if (cc == 1 && (pass == 3 || pass == 5)) mbar_arrive(&bars[isy ? B_Y2_FREE : B_X2_FREE]);
+            if (cc == 1 && (pass == 3 || pass == 5)) mbar_arrive_s(bar0 + 8 * (isy ? B_Y2_FREE : B_X2_FREE));
             continue;
           }
           tmem_ld16(trow + (isy ? CFC_Y2 : CFC_X2) + n0 + 16 * cc, v);
           wait_ld();
           if (cc == 1 && (pass == 3 || pass == 5)) {   // the accumulator of this net is drained: layer 2 of the next tile may overwrite it
             fence_before_sync();
-            mbar_arrive(&bars[isy ? B_Y2_FREE : B_X2_FREE]);
+            mbar_arrive_s(bar0 + 8 * (isy ? B_Y2_FREE : B_X2_FREE));
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -414,7 +453,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
 #pragma unroll
           for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(a.filt + r * 192 + 32 * pass + 4 * q) = dstW[q];
         }
-        mbar_arrive(&bars[B_FULL0 + b]);
+        mbar_arrive_s(bar0 + 8 * (B_FULL0 + b));
         pc.tick(3);
       }
     }
@@ -427,27 +466,29 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
     // run is rq mod 4, in order; lanes = float4 columns of the 32-column pass.  Summation order == cfconv_aggregate_kernel
     // (schnet.cu).  The x rows of the warp's first two runs are requested one pass ahead; steps past the end of a run carry
     // x = 0 and the W of the run's last row, so the unconditional fmaf leaves the sum unchanged.
+    const uint32_t sb = cf_sbase(), bar0 = sb + CFO_BARS;
+    float* s_W = reinterpret_cast<float*>(cf_generic(sb + CFO_W));
+    float* s_carry = s_W + 2 * TM * LDS_Q;
+    int* s_bk = reinterpret_cast<int*>(s_carry + 2 * 4 * 192);
+    int* s_meta = s_bk + 2 * CF_BKS;
     const int team = (warp - CF_WARP_R) / CF_RWARPS, rw = (warp - CF_WARP_R) % CF_RWARPS;
     const int rq = lane >> 3, c4 = (lane & 7) * 4;
     auto item_of = [&](int k, int jt) {
-      const int* bdst_ = s_bk + (jt & 1) * 3 * TM + TM;
-      const int* bruns = bdst_ + TM;
+      const int* bdst_ = s_bk + (jt & 1) * CF_BKS + TM;
+      const int* bruns = bdst_ + TM;   // run starts, closed by the number of valid rows
       const int* meta = s_meta + (jt & 1) * 4;
-      const int64_t rowt = cta_begin + static_cast<int64_t>(jt) * TM;
-      const int nv = (cta_end - rowt < TM) ? static_cast<int>(cta_end - rowt) : TM;
       const int n_runs = meta[0];
       CfItem it;
       if (k < n_runs) {
         const int s = bruns[k];
-        it.s = s;
-        it.e = (k + 1 < n_runs) ? bruns[k + 1] : nv;
+        it.e = bruns[k + 1];
         const int base = (k == 0) ? meta[3] : s;
         it.first = s + ((rq - (s - base)) & 3);
         it.dst_off = bdst_[s] * 192;
         it.cin = (k == 0) && meta[1] != 0;
         it.cout = (k == n_runs - 1) && meta[2] != 0;
       } else {
-        it.s = it.first = it.e = it.dst_off = 0;
+        it.first = it.e = it.dst_off = 0;
         it.cin = it.cout = false;
       }
       return it;
@@ -455,10 +496,9 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
     // x values of the rows first + 4 u of this warp's run for its next pass.  A team only works on every other pass, so a request
     // issued right after a pass has a whole slab period of the other team to arrive before it is consumed.
     float4 xv[CF_STEPS];
-    CfItem cur, nxt;   // the run of the current / the next tile
-    cur.s = cur.first = cur.e = cur.dst_off = 0;
+    CfItem cur;   // this warp's run of the current tile (replaced by the next tile's once the team's last pass is done)
+    cur.first = cur.e = cur.dst_off = 0;
     cur.cin = cur.cout = false;
-    nxt = cur;
     PhaseClock pc;
     pc.start(a.timing != nullptr && lane == 0 && rw == 0 && team == 0);
     const bool skip_gather = (a.debug_filt & 2) != 0;
@@ -474,18 +514,17 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
       if (rr < e_) xv[u] = __ldg(reinterpret_cast<const float4*>(px_ + (bsrc_)[rr]));                                \
     }                                                                                                                \
   }
-    uint64_t* full = &bars[B_FULL0 + team];
-    uint64_t* empty = &bars[B_EMPTY0 + team];
+    const uint32_t full = bar0 + 8 * (B_FULL0 + team), empty = bar0 + 8 * (B_EMPTY0 + team);
     const float* sw = s_W + team * (TM * LDS_Q) + c4;   // the team's slab
     uint32_t n_use = 0;
     if (T > 0) {
-      mbar_wait(&bars[B_BK_FULL0], 0u);
+      mbar_wait_s(bar0 + 8 * B_BK_FULL0, 0u);
       cur = item_of(rw, 0);
       CF_REQUEST(cur, s_bk, 32 * team + c4);
     }
     for (int j = 0; j < T; ++j) {
       const int n_runs = s_meta[(j & 1) * 4];
-      const int* bsrc = s_bk + (j & 1) * 3 * TM;
+      const int* bsrc = s_bk + (j & 1) * CF_BKS;
       const bool more = j + 1 < T;
       pc.tick(0);
 #pragma unroll 1
@@ -493,7 +532,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
         const int col = 32 * pass + c4;
         float* carry_w = s_carry + (j & 1) * 768 + rq * 192 + col;              // written in this tile, read in the next
         const float* carry_r = s_carry + ((j & 1) ^ 1) * 768 + rq * 192 + col;
-        mbar_wait(full, n_use & 1u);
+        mbar_wait_s(full, n_use & 1u);
         pc.tick(1);
         if (rw < n_runs && !(a.debug_filt & 4)) {
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -520,26 +559,31 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty);   // the slab may be refilled
+        if (lane == 0) mbar_arrive_s(empty);   // the slab may be refilled
         pc.tick(2);
         if (pass + 2 < 6) {
           CF_REQUEST(cur, bsrc, col + 64);
         } else if (more) {   // the next tile's run: its bookkeeping is published by the loader, which runs a tile ahead
-          mbar_wait(&bars[B_BK_FULL0 + ((j + 1) & 1)], static_cast<uint32_t>((j + 1) >> 1) & 1u);
-          nxt = item_of(rw, j + 1);
-          const int* bsrc_n = s_bk + ((j + 1) & 1) * 3 * TM;
-          CF_REQUEST(nxt, bsrc_n, 32 * team + c4);
+          mbar_wait_s(bar0 + 8 * (B_BK_FULL0 + ((j + 1) & 1)), static_cast<uint32_t>((j + 1) >> 1) & 1u);
+          cur = item_of(rw, j + 1);
+          const int* bsrc_n = s_bk + ((j + 1) & 1) * CF_BKS;
+          CF_REQUEST(cur, bsrc_n, 32 * team + c4);
         }
         pc.tick(3);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[B_BK_FREE0 + (j & 1)]);
-      cur = nxt;
+      if (lane == 0) mbar_arrive_s(bar0 + 8 * (B_BK_FREE0 + (j & 1)));
     }
 #undef CF_REQUEST
     pc.flush(a.timing, 2);
     } else if (warp == CF_WARP_M && T > 0) {
     // ================================================================== M: weights + MMA issue (warp-uniform, elect inside)
+    const uint32_t sb = cf_sbase(), bar0 = sb + CFO_BARS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cf_generic(bar0));
+    uint8_t* w1x = cf_generic(sb);
+    uint8_t* w1y = w1x + CF_W1X;
+    uint8_t* w2x = w1y + CF_W1Y;
+    uint8_t* w2y = w2x + CF_W2X;
     if (lane == 0) {
       mbar_expect_tx(&bars[B_W], CF_W1X + CF_W1Y + CF_W2X + CF_W2Y);
       const uint8_t* p;
@@ -553,34 +597,34 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
       for (uint32_t off = 0; off < CF_W2Y; off += 16384) bulk_g2s(w2y + off, p + off, 16384, &bars[B_W]);
     }
     __syncwarp();
-    mbar_wait(&bars[B_W], 0);
+    mbar_wait_s(bar0 + 8 * B_W, 0);
     // weight descriptors: the four [hi | lo'] images follow each other from `base`, so each is the first plus a constant
-    const uint64_t d1x = smem_desc_sw128(smem_u32(base));
+    const uint64_t d1x = smem_desc_sw128(sb);
     const uint64_t d1y = d1x + (CF_W1X >> 4), d2x = d1y + (CF_W1Y >> 4), d2y = d2x + (CF_W2X >> 4);
     PhaseClock pc;
     pc.start(a.timing != nullptr && lane == 0);
 #pragma unroll 1
     for (int j = 0; j < T; ++j) {
       const uint32_t ph = static_cast<uint32_t>(j) & 1u;
-      mbar_wait(&bars[B_A1_FULL], ph);
+      mbar_wait_s(bar0 + 8 * B_A1_FULL, ph);
       fence_after_sync();
       pc.tick(0);
-      cf_issue<HID, 128, false, CFC_X1, CFC_A1HI, CFC_A1LO>(d1x, scaled, &bars[B_D1X]);
-      cf_issue<HID, 64, false, CFC_Y1, CFC_A1HI, CFC_A1LO>(d1y, scaled, &bars[B_D1Y], &bars[B_A1_FREE]);
+      cf_issue<HID, 128, false, CFC_X1, CFC_A1HI, CFC_A1LO>(d1x, scaled, bar0 + 8 * B_D1X);
+      cf_issue<HID, 64, false, CFC_Y1, CFC_A1HI, CFC_A1LO>(d1y, scaled, bar0 + 8 * B_D1Y, bar0 + 8 * B_A1_FREE);
       pc.tick(1);
-      mbar_wait(&bars[B_A2X], ph);
+      mbar_wait_s(bar0 + 8 * B_A2X, ph);
       pc.tick(2);
-      if (j > 0) mbar_wait(&bars[B_X2_FREE], ph ^ 1u);
+      if (j > 0) mbar_wait_s(bar0 + 8 * B_X2_FREE, ph ^ 1u);
       fence_after_sync();
       pc.tick(3);
-      cf_issue<128, 128, true, CFC_X2, CFC_X1, 0u>(d2x, scaled, &bars[B_D2X]);
+      cf_issue<128, 128, true, CFC_X2, CFC_X1, 0u>(d2x, scaled, bar0 + 8 * B_D2X);
       pc.tick(4);
-      mbar_wait(&bars[B_A2Y], ph);
+      mbar_wait_s(bar0 + 8 * B_A2Y, ph);
       pc.tick(5);
-      if (j > 0) mbar_wait(&bars[B_Y2_FREE], ph ^ 1u);
+      if (j > 0) mbar_wait_s(bar0 + 8 * B_Y2_FREE, ph ^ 1u);
       fence_after_sync();
       pc.tick(6);
-      cf_issue<64, 64, true, CFC_Y2, CFC_Y1, 0u>(d2y, scaled, &bars[B_D2Y]);
+      cf_issue<64, 64, true, CFC_Y2, CFC_Y1, 0u>(d2y, scaled, bar0 + 8 * B_D2Y);
       pc.tick(7);
     }
     pc.flush(a.timing, 4);
@@ -588,6 +632,9 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
   } else {
     reg_dec<56>();
     // ================================================================== L: operand loader + bookkeeping
+    const uint32_t sb = cf_sbase(), bar0 = sb + CFO_BARS;
+    int* s_bk = reinterpret_cast<int*>(cf_generic(sb + CFO_BK));
+    int* s_meta = s_bk + 2 * CF_BKS;
     const int quad = warp & 3;
     const int my_row = quad * 32 + lane;
     const uint32_t trow = static_cast<uint32_t>(quad * 32) << 16;
@@ -597,7 +644,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
     // Bookkeeping of tile jn -> s_bk[jn & 1]: x-row offsets and destinations of the rows, run starts, and whether the first / last
     // run continues across the tile boundary.  Published through B_BK_FULL; the buffer was released by the reducers two tiles ago.
     auto bookkeep = [&](int jn) {
-      int* bsrc = s_bk + (jn & 1) * 3 * TM;
+      int* bsrc = s_bk + (jn & 1) * CF_BKS;
       int* bdst = bsrc + TM;
       int* bruns = bdst + TM;
       const int64_t rown = cta_begin + static_cast<int64_t>(jn) * TM;
@@ -609,7 +656,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
         if (jn > 0) prev_dst = __ldg(a.e_dst + rown - 1);
         if (rown + nv < cta_end) next_dst = __ldg(a.e_dst + rown + nv);
       }
-      if (jn >= 2) mbar_wait(&bars[B_BK_FREE0 + (jn & 1)], static_cast<uint32_t>((jn >> 1) - 1) & 1u);
+      if (jn >= 2) mbar_wait_s(bar0 + 8 * (B_BK_FREE0 + (jn & 1)), static_cast<uint32_t>((jn >> 1) - 1) & 1u);
       bsrc[my_row] = src;
       bdst[my_row] = dst;
       group_sync(2, 128);
@@ -625,6 +672,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
           if (start) bruns[n_runs + __popc(m & ((1u << lane) - 1u))] = row;
           n_runs += __popc(m);
         }
+        if (lane == 0) bruns[n_runs] = nv;   // closes the last run
         const int d0 = bdst[0];
         const bool cin = (d0 == prev_dst);
         // tile row at which run 0 began (<= 0: in an earlier tile): positions in a run are counted from its first edge
@@ -637,7 +685,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
           meta[3] = base0;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[B_BK_FULL0 + (jn & 1)]);
+        if (lane == 0) mbar_arrive_s(bar0 + 8 * (B_BK_FULL0 + (jn & 1)));
       }
     };
     for (int j = 0; j < T; ++j) {
@@ -663,7 +711,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
         }
         if (ch == 0 && j > 0) {   // layer 1 of the previous tile has read the operand columns
           pc.tick(0);
-          mbar_wait(&bars[B_A1_FREE], static_cast<uint32_t>(j - 1) & 1u);
+          mbar_wait_s(bar0 + 8 * B_A1_FREE, static_cast<uint32_t>(j - 1) & 1u);
           fence_after_sync();
           pc.tick(1);
         }
@@ -678,7 +726,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
       }
       wait_st();
       fence_before_sync();
-      mbar_arrive(&bars[B_A1_FULL]);
+      mbar_arrive_s(bar0 + 8 * B_A1_FULL);
       pc.tick(2);
       bookkeep(j);   // the loader runs a tile ahead of the reducers: never urgent
       pc.tick(3);
