@@ -23,7 +23,7 @@ EXPORTS = [
     "agd_batch_create", "agd_batch_destroy", "agd_build_edges", "agd_forward", "agd_sample",
     "agd_extend_bond_order", "agd_op_cfconv_aggregate", "agd_op_eq_transform", "agd_debug_fetch",
     "agd_launch_count", "agd_profile_forward", "agd_forward_edges",
-    "agd_set_mode", "agd_get_mode", "agd_set_option", "agd_range_flag", "agd_f16_lo_shift", "agd_debug_timing",
+    "agd_nan_steps", "agd_set_mode", "agd_get_mode", "agd_set_option", "agd_range_flag", "agd_f16_lo_shift", "agd_debug_timing",
 ]
 
 
@@ -114,6 +114,8 @@ def load() -> C.CDLL:
     lib.agd_set_mode.argtypes = [vp, C.c_int]
     lib.agd_get_mode.argtypes = [vp]
     lib.agd_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.agd_nan_steps.argtypes = [vp, vp, C.c_int32]
+    lib.agd_nan_steps.restype = C.c_int
     lib.agd_range_flag.argtypes = [vp, C.POINTER(i32)]
     lib.agd_f16_lo_shift.restype = C.c_int
     lib.agd_debug_timing.argtypes = [vp, vp]

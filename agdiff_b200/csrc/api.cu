@@ -52,7 +52,8 @@ struct agd_handle {
   int64_t n_weights = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_poll[2] = {nullptr, nullptr};
+  int* poll_flag = nullptr;   // pinned host copies [2] of the first-NaN-step counter (early exit of agd_sample)
   int64_t launches = 0;
   int f16_fuse = 1;
   int f16_mlp = 1;
@@ -237,6 +238,9 @@ int agd_create(const agd_config* cfg, agd_handle** out) {
   CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_poll[0], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_poll[1], cudaEventDisableTiming));
+  CUDA_TRY(cudaMallocHost(&h->poll_flag, 2 * sizeof(int)));
   set_encoder_attributes();
   set_schnet_attributes();
   set_gin_attributes();
@@ -265,6 +269,9 @@ void agd_destroy(agd_handle* h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
+  if (h->ev_poll[0]) cudaEventDestroy(h->ev_poll[0]);
+  if (h->ev_poll[1]) cudaEventDestroy(h->ev_poll[1]);
+  if (h->poll_flag) cudaFreeHost(h->poll_flag);
   delete h;
 }
 
@@ -322,6 +329,7 @@ static void carve(BatchDev& d, Carver& c) {
   d.in_ptr = c.take<int>(N + 1);
   d.out_ptr = c.take<int>(N + 1);
   d.counters = c.take<int>(8);
+  d.nan_mol = c.take<int>((size_t)(d.n_mols > 0 ? d.n_mols : 1));
   d.e_src = c.take<int>(E);
   d.e_dst = c.take<int>(E);
   d.e_type = c.take<int>(E);
@@ -366,6 +374,7 @@ int64_t agd_batch_workspace_bytes(const agd_handle* h, const agd_batch_desc* d) 
   if (check_desc(d) != AGD_OK) return -1;
   BatchDev t{};
   t.n_atoms = d->n_atoms;
+  t.n_mols = d->n_mols;
   t.cap = d->edge_capacity;
   t.n_local = d->n_local;
   Carver c{nullptr};
@@ -489,10 +498,41 @@ int agd_sample(agd_handle* h, agd_batch* b, float* pos, const agd_sample_params*
   if (p->n_steps == 0) return AGD_OK;
   if ((rc = enter(h, stream))) return rc;
   BatchDev& d = b->d;
+
+  // Everything below runs on h->stream between enter() and leave().  Whatever way the function is left - a CUDA error in the
+  // middle of a stream capture included - the guard ends the capture, destroys the instantiated graphs and re-joins the caller's
+  // stream, so the handle stays usable.
+  struct Guard {
+    agd_handle* h;
+    void* user_stream;
+    cudaGraphExec_t exec_one[2] = {nullptr, nullptr};
+    cudaGraphExec_t exec_chunk[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    bool left = false;
+    ~Guard() {
+      cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(h->stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+        cudaGraph_t g = nullptr;
+        cudaStreamEndCapture(h->stream, &g);
+        if (g) cudaGraphDestroy(g);
+      }
+      for (int g = 0; g < 2; ++g) {
+        if (exec_one[g]) cudaGraphExecDestroy(exec_one[g]);
+        for (int k = 0; k < 2; ++k)
+          if (exec_chunk[g][k]) cudaGraphExecDestroy(exec_chunk[g][k]);
+      }
+      if (!left) {
+        cudaEventRecord(h->ev_out, h->stream);
+        cudaStreamWaitEvent((cudaStream_t)user_stream, h->ev_out, 0);
+        cudaGetLastError();
+      }
+    }
+  } guard{h, stream};
+
   // per-step schedule -> device
   if (d.sched_cap < p->n_steps) {
     if (d.sched) CUDA_TRY(cudaFree(d.sched));
     d.sched = nullptr;
+    d.sched_cap = 0;
     CUDA_TRY(cudaMalloc(&d.sched, sizeof(float) * 4 * (size_t)p->n_steps));
     d.sched_cap = p->n_steps;
   }
@@ -506,6 +546,7 @@ int agd_sample(agd_handle* h, agd_batch* b, float* pos, const agd_sample_params*
   CUDA_TRY(cudaMemcpyAsync(d.sched, sched.data(), sizeof(float) * sched.size(), cudaMemcpyHostToDevice, h->stream));
   const int init[5] = {0, 0, INT_MAX, 0, 0};
   CUDA_TRY(cudaMemcpyAsync(d.counters, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemsetAsync(d.nan_mol, 0x7f, sizeof(int) * (size_t)d.n_mols, h->stream));   // AGD_NAN_NONE = 0x7f7f7f7f
   CUDA_TRY(cudaStreamSynchronize(h->stream));  // `sched`/`init` are stack/heap temporaries
 
   LaunchCtx c = make_ctx(h);
@@ -522,6 +563,29 @@ int agd_sample(agd_handle* h, agd_batch* b, float* pos, const agd_sample_params*
   bool any_global = false, any_local = false;
   for (int s = 0; s < p->n_steps; ++s) (p->use_global[s] ? any_global : any_local) = true;
 
+  // NaN guard (dualenc.py:539-541) without a host sync per step: the launches are issued in windows of POLL; behind every
+  // window the first-NaN-step counter is copied to pinned memory and an event is recorded, and before issuing window w + 1 the
+  // host waits for the event of window w - 1.  The GPU always has a full window queued, the host is never more than two windows
+  // ahead, and a diverged call stops within ~2 windows instead of running all 5000 steps.
+  const int POLL = 8;
+  h->poll_flag[0] = h->poll_flag[1] = INT_MAX;
+  bool nan_seen = false;
+  int since_poll = 0, window = 0;
+  auto poll = [&]() -> cudaError_t {
+    if (++since_poll < POLL) return cudaSuccess;
+    since_poll = 0;
+    const int w = window & 1;
+    cudaError_t e = cudaMemcpyAsync(h->poll_flag + w, d.counters + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaEventRecord(h->ev_poll[w], h->stream)) != cudaSuccess) return e;
+    if (window >= 1) {
+      if ((e = cudaEventSynchronize(h->ev_poll[w ^ 1])) != cudaSuccess) return e;
+      if (h->poll_flag[w ^ 1] != INT_MAX) nan_seen = true;
+    }
+    ++window;
+    return cudaSuccess;
+  };
+
   if (p->use_cuda_graph) {
     // Per step type (local-only / local+global) two graphs are captured: one step, and a chunk of CHUNK consecutive steps
     // (the device-side step counter makes a multi-step graph valid for any run of equal-type steps).  A graph launch costs
@@ -530,16 +594,7 @@ int agd_sample(agd_handle* h, agd_batch* b, float* pos, const agd_sample_params*
     // chunk graph are launched alternately.
     int chunk = 8;
     if (const char* e = std::getenv("AGD_GRAPH_CHUNK")) chunk = std::atoi(e) > 0 ? std::atoi(e) : 1;
-    cudaGraphExec_t exec_one[2] = {nullptr, nullptr};
-    cudaGraphExec_t exec_chunk[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     int64_t per_step_launches[2] = {0, 0};
-    auto destroy_all = [&]() {
-      for (int g = 0; g < 2; ++g) {
-        if (exec_one[g]) cudaGraphExecDestroy(exec_one[g]);
-        for (int k = 0; k < 2; ++k)
-          if (exec_chunk[g][k]) cudaGraphExecDestroy(exec_chunk[g][k]);
-      }
-    };
     // longest run of equal-type steps decides whether a chunk graph is worth building
     int longest[2] = {0, 0};
     for (int s = 0; s < p->n_steps;) {
@@ -560,54 +615,65 @@ int agd_sample(agd_handle* h, agd_batch* b, float* pos, const agd_sample_params*
         cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
         if (kind == 0) per_step_launches[g] = h->launches - before;
         h->launches = before;
-        if (e != cudaSuccess) { destroy_all(); return fail(AGD_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e)); }
-        if (kind == 0) e = cudaGraphInstantiate(&exec_one[g], graph, 0);
+        if (e != cudaSuccess) return fail(AGD_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        if (kind == 0) e = cudaGraphInstantiate(&guard.exec_one[g], graph, 0);
         else
-          for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaGraphInstantiate(&exec_chunk[g][k], graph, 0);
+          for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaGraphInstantiate(&guard.exec_chunk[g][k], graph, 0);
         cudaGraphDestroy(graph);
-        if (e != cudaSuccess) { destroy_all(); return fail(AGD_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e)); }
+        if (e != cudaSuccess) return fail(AGD_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
       }
     }
     cudaError_t e = cudaSuccess;
     int flip = 0;
-    for (int s = 0; s < p->n_steps && e == cudaSuccess;) {
+    for (int s = 0; s < p->n_steps && e == cudaSuccess && !nan_seen;) {
       const int g = p->use_global[s] ? 1 : 0;
       int run = 1;
       while (run < chunk && s + run < p->n_steps && (p->use_global[s + run] != 0) == (g == 1)) ++run;
-      if (run == chunk && exec_chunk[g][0]) {
-        e = cudaGraphLaunch(exec_chunk[g][flip], h->stream);
+      if (run == chunk && guard.exec_chunk[g][0]) {
+        e = cudaGraphLaunch(guard.exec_chunk[g][flip], h->stream);
         flip ^= 1;
         h->launches += per_step_launches[g] * chunk;
         s += chunk;
       } else {
-        e = cudaGraphLaunch(exec_one[g], h->stream);
+        e = cudaGraphLaunch(guard.exec_one[g], h->stream);
         h->launches += per_step_launches[g];
         s += 1;
       }
+      if (e == cudaSuccess) e = poll();
     }
     cudaError_t e2 = cudaStreamSynchronize(h->stream);
-    destroy_all();
     if (e != cudaSuccess) return fail(AGD_ERR_CUDA, std::string("graph launch: ") + cudaGetErrorString(e));
     if (e2 != cudaSuccess) return fail(AGD_ERR_CUDA, std::string("sampling loop: ") + cudaGetErrorString(e2));
   } else {
-    for (int s = 0; s < p->n_steps; ++s) one_step(p->use_global[s] != 0);
+    for (int s = 0; s < p->n_steps && !nan_seen; ++s) {
+      one_step(p->use_global[s] != 0);
+      CUDA_TRY(poll());
+    }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
   CUDA_TRY(cudaGetLastError());
   if ((rc = check_overflow(b))) return rc;
   int range_flag = 0;
   CUDA_TRY(cudaMemcpy(&range_flag, d.counters + 4, sizeof(int), cudaMemcpyDeviceToHost));
-  if (range_flag) {
-    if ((rc = leave(h, stream))) return rc;
-    return fail(AGD_ERR_RANGE, "an activation left the fp16-split range; re-run in AGD_MODE_TF32");
-  }
   int nan_step = INT_MAX;
   CUDA_TRY(cudaMemcpy(&nan_step, d.counters + 2, sizeof(int), cudaMemcpyDeviceToHost));
+  guard.left = true;
   if ((rc = leave(h, stream))) return rc;
+  if (range_flag) return fail(AGD_ERR_RANGE, "an activation left the fp16-split range; re-run in AGD_MODE_TF32");
   if (nan_step != INT_MAX) {
     if (first_nan_step) *first_nan_step = nan_step;
     return fail(AGD_ERR_NAN, "NaN positions at sampling step " + std::to_string(nan_step));
   }
+  return AGD_OK;
+}
+
+int agd_nan_steps(agd_batch* b, int32_t* host_out, int32_t n_mols) {
+  if (!b || !host_out || n_mols != b->d.n_mols) return fail(AGD_ERR_INVALID, "agd_nan_steps: bad arguments");
+  CUDA_TRY(cudaSetDevice(b->h->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(b->h->stream));
+  CUDA_TRY(cudaMemcpy(host_out, b->d.nan_mol, sizeof(int) * (size_t)n_mols, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n_mols; ++i)
+    if (host_out[i] == 0x7f7f7f7f) host_out[i] = -1;
   return AGD_OK;
 }
 

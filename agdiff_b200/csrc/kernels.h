@@ -77,6 +77,7 @@ struct BatchDev {
   int *in_deg, *out_deg;         // [N]
   int *in_ptr, *out_ptr;         // [N+1]
   int* counters;                 // [0]=n_edges [1]=step index [2]=first NaN step
+  int* nan_mol;                  // [n_mols] first NaN step of each molecule (agd_nan_steps)
   // radius-extended edges, CSC order (grouped by destination)
   int *e_src, *e_dst, *e_type, *e_canon;
   float* e_len;

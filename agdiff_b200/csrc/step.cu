@@ -57,6 +57,7 @@ struct StepArgs {
   const float *lclen, *sl_canon;
   const float* sched;
   int* counters;
+  int* nan_mol;   // [n_mols] first step at which the molecule's positions became NaN (INT_MAX: never)
   StepParams p;
 };
 
@@ -149,7 +150,8 @@ __global__ void __launch_bounds__(STEP_THREADS) langevin_step_kernel(const StepA
   if ((tid & 31) == 0) {
     red[0][tid >> 5] = sx; red[1][tid >> 5] = sy; red[2][tid >> 5] = sz;
   }
-  __syncthreads();   // also: every thread has finished reading the old positions
+  const int any_bad = __syncthreads_or(bad ? 1 : 0);   // also: every thread has finished reading the old positions
+  if (any_bad && tid == 0) atomicMin(&a.nan_mol[m], step);
   float cx = 0.f, cy = 0.f, cz = 0.f;
 #pragma unroll
   for (int w = 0; w < STEP_THREADS / 32; ++w) { cx += red[0][w]; cy += red[1][w]; cz += red[2][w]; }
@@ -188,6 +190,7 @@ void launch_step(const LaunchCtx& c, const BatchDev& b, float* pos, const StepPa
   a.lout_ptr = b.lc_out_ptr; a.lcdst = b.lc_cdst; a.lclen = b.lcc_len; a.sl_canon = b.sl_canon;
   a.sched = b.sched;
   a.counters = b.counters;
+  a.nan_mol = b.nan_mol;
   a.p = p;
   langevin_step_kernel<<<b.n_mols, STEP_THREADS, 0, c.stream>>>(a);
   note_launch(c, "step.langevin");

@@ -48,12 +48,24 @@ def gather_positions(pos_local: torch.Tensor, my_mols: Sequence[int], sizes: Seq
 
 
 def sample_sharded(sampler: Callable, mols: List[Molecule], repeats: int, pos_init: torch.Tensor, device,
-                   group=None, **sampler_kwargs) -> torch.Tensor:
+                   group=None, *, seed: int = None, **sampler_kwargs) -> torch.Tensor:
     """Shard ``mols`` (each sampled ``repeats`` times) over the ranks of ``group``, run ``sampler`` (a
     bound ``langevin_dynamics_sample_diffusion``) on the local shard and gather the final positions.
-    ``pos_init`` is the full (sum n_i * repeats, 3) initial noise in global conformer order."""
+    ``pos_init`` is the full (sum n_i * repeats, 3) initial noise in global conformer order.
+
+    ``seed`` keys the Langevin noise streams (together with the global conformer ids) and must be the same on every rank for
+    the result to be independent of the rank count: when it is not given, rank 0 draws one from its torch generator and
+    broadcasts it."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if seed is None and "noise" not in sampler_kwargs:
+        t = torch.empty((), dtype=torch.int64).random_()
+        if world > 1:
+            t = t.to(device) if dist.get_backend(group) == "nccl" else t
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        seed = int(t.item()) & 0x7FFFFFFFFFFFFFFF
+    if seed is not None:
+        sampler_kwargs = dict(sampler_kwargs, seed=int(seed))
     sizes = [m.num_nodes for m in mols]
     parts = shard_molecules(sizes, world)
     mine = parts[rank]

@@ -11,7 +11,10 @@ and no CPU fallback.
 
 Extensions (keyword-only, all optional, defaults reproduce the reference behaviour):
   noise=(n_steps,N,3) tensor   inject the Langevin noise instead of drawing it (parity tests)
-  seed=int                     Philox seed for the device noise generator
+  seed=int                     Philox seed for the device noise generator.  Default: a fresh draw from torch's global CPU
+                               generator per call, so successive calls use different noise (like torch.randn_like in the
+                               reference) yet stay reproducible under torch.manual_seed; pass seed (+ mol_gid) for a
+                               stream that does not depend on call order.
   return_traj=bool             False skips the per-step trajectory (reference always keeps it)
   mol_gid=(G,) int64           global molecule ids keying the noise streams (multi-GPU sharding)
   use_cuda_graph=bool          replay captured per-step graphs (default True)
@@ -21,6 +24,7 @@ Extensions (keyword-only, all optional, defaults reproduce the reference behavio
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 from typing import List, Optional
 
 import numpy as np
@@ -451,10 +455,21 @@ class DualEncoderEpsNetwork(nn.Module):
             if bool((w[used].norm(dim=1) > 10.0).any()):
                 torch.embedding_renorm_(w, used.contiguous(), 10.0, 2.0)
 
+    def _warn_if_training(self):
+        """The kernels fold BatchNorm with its running statistics (eval semantics, what sampling uses: dualenc.py:471 calls
+        self.eval()).  In train mode the reference normalises with batch statistics instead - say so once rather than return
+        different numbers silently."""
+        if self.training and not getattr(self, "_warned_training", False):
+            self._warned_training = True
+            warnings.warn("agdiff_b200 evaluates BatchNorm with running statistics (eval semantics) and builds no autograd graph; "
+                          "call .eval() - forward()/get_loss() of a module in train mode differ from the reference's train-mode "
+                          "values", RuntimeWarning, stacklevel=3)
+
     # ------------------------------------------------------------------ forward
     def forward(self, atom_type, pos, bond_index, bond_type, batch, time_step, edge_index=None, edge_type=None,
                 edge_length=None, return_edges=False, extend_order=True, extend_radius=True):
         """reference dualenc.py:142-251; ``time_step`` is unused there as well."""
+        self._warn_if_training()
         dev = self._device()
         atom_type = atom_type.to(dev)
         self._renorm_embedding(atom_type)
@@ -584,6 +599,7 @@ class DualEncoderEpsNetwork(nn.Module):
         position perturbation, the score network on the perturbed positions, four eq_transforms, per-atom loss.  The native
         path has no autograd, so the result carries no graph - training stays with the reference.  Extensions: ``time_step=``
         (G,) and ``pos_noise=`` (N,3) inject the two random draws (defaults draw them exactly like the reference does)."""
+        self._warn_if_training()
         dev = self._device()
         atom_type, pos, batch = atom_type.to(dev), pos.to(dev, torch.float32), batch.to(dev)
         node2graph = batch
@@ -660,10 +676,11 @@ class DualEncoderEpsNetwork(nn.Module):
                                            w_global=0.2, w_reg=1.0, **kwargs):
         """reference dualenc.py:441-547.  Returns (pos, pos_traj) with pos on the model's device and
         pos_traj a list of n_steps CPU tensors (empty when return_traj=False)."""
-        if not extend_radius:
-            raise NotImplementedError("extend_radius=False is not on the native path")
         noise = kwargs.get("noise")
-        seed = int(kwargs.get("seed", torch.initial_seed() & 0x7FFFFFFFFFFFFFFF))
+        seed = kwargs.get("seed")
+        if seed is None:    # fresh per call, reproducible under torch.manual_seed (the reference draws torch.randn_like per step)
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        seed = int(seed) & 0x7FFFFFFFFFFFFFFF
         return_traj = bool(kwargs.get("return_traj", True))
         use_graph = bool(kwargs.get("use_cuda_graph", True))
         t_start = kwargs.get("t_start")            # extension: run a window of the schedule
@@ -675,6 +692,12 @@ class DualEncoderEpsNetwork(nn.Module):
         self._renorm_embedding(atom_type)
         self._sync_weights()
         sigmas, sig, stp, nsc, glb = self.step_schedule(n_steps, step_lr, global_start_sigma, t_start)
+        if not extend_radius:
+            # Without the radius graph every edge is a bond / 2-hop / 3-hop edge, i.e. local: the reference masks ALL global edge
+            # scores to zero (dualenc.py:516-517), eq_transform of zeros is zero and so is its clip_norm - the global branch
+            # contributes exactly nothing, so it is not evaluated.  (Only difference: a non-finite global score would turn into
+            # NaN * 0 = NaN there and raise FloatingPointError; the local branch raises on its own NaNs as usual.)
+            glb[:] = 0
         with torch.no_grad():
             pos = pos_init.to(dev, torch.float32)
             pos = (pos * sigmas[-1].to(dev)) if scale_init else pos.clone()
@@ -745,7 +768,12 @@ class DualEncoderEpsNetwork(nn.Module):
                                                     self._stream())
                         if rc == _lib.AGD_ERR_NAN:
                             print("NaN detected. Please restart.")
-                            raise FloatingPointError()
+                            err = FloatingPointError()
+                            steps = np.zeros(g1 - g0, np.int32)     # which conformers went NaN (extension: lets batched callers
+                            if lib.agd_nan_steps(nb.handle, steps.ctypes.data_as(C.c_void_p), g1 - g0) == 0:    # retry only those)
+                                err.bad_graphs = [g0 + int(k) for k in np.nonzero(steps >= 0)[0]]
+                                err.first_nan_step = int(nan_step.value) + s0
+                            raise err
                         _lib.check(rc)
                         if tbuf is not None:
                             traj_host[s0:s1, a0:a1].copy_(tbuf[: s1 - s0], non_blocking=True)

@@ -58,15 +58,25 @@ def plan_batches(sizes: Sequence[int], samples: Sequence[int], max_atoms: int) -
     return batches
 
 
+def initial_positions(index: int, n_rows: int, seed: int = 2021) -> torch.Tensor:
+    """pos_init ~ N(0, 1) of one molecule's conformers (scripts/test.py:147), from a generator keyed by the molecule's index in
+    the job so that it does not depend on how molecules are grouped into sampler calls"""
+    g = torch.Generator().manual_seed(int(seed) * 1000003 + int(index))
+    return torch.randn(n_rows, 3, generator=g)
+
+
 def sample_conformers(model, mols: Sequence[Molecule], num_samples: Union[int, Sequence[int], Callable[[int], int]] = 2, *,
                       n_steps: int = 5000, w_global: float = 1.0, global_start_sigma: float = 0.5, clip: float = 1000.0,
                       step_lr: float = 1e-6, sampling_type: str = "ld", eta: float = 1.0, save_traj: bool = False,
                       extend_order_offline: bool = True, edge_order: Optional[int] = None, max_atoms_per_call: int = 40000,
                       seed: int = 2021, device=None, done: Iterable[int] = (), retry_clip_local: float = 20.0,
-                      on_result: Optional[Callable[[SampleResult], None]] = None) -> List[Optional[SampleResult]]:
+                      on_result: Optional[Callable[[SampleResult], None]] = None,
+                      noise_fn: Optional[Callable[[int, int], torch.Tensor]] = None) -> List[Optional[SampleResult]]:
     """Sample ``num_samples`` conformers of every molecule (defaults = ``scripts/test.py:46-60``).  ``mols`` carry the plain
     bond graph when ``extend_order_offline`` (the order-3 extension is applied here, like the dataset transform does), or the
-    already extended one.  Returns one ``SampleResult`` per molecule (``None`` for indices listed in ``done``)."""
+    already extended one.  Returns one ``SampleResult`` per molecule (``None`` for indices listed in ``done``).
+    ``noise_fn(index, n_rows) -> (n_steps, n_rows, 3)`` injects the Langevin noise of one molecule's conformers (parity tests);
+    by default it is drawn on the device from Philox streams keyed by the global conformer id."""
     device = device if device is not None else next(model.parameters()).device
     order = int(edge_order if edge_order is not None else getattr(model.config, "edge_order", 3))
     ext = [extend_bond_order_host(m, order) if extend_order_offline else m for m in mols]
@@ -84,8 +94,7 @@ def sample_conformers(model, mols: Sequence[Molecule], num_samples: Union[int, S
     results: List[Optional[SampleResult]] = [None] * len(ext)
 
     def pos_init_of(i: int) -> torch.Tensor:
-        g = torch.Generator().manual_seed(int(seed) * 1000003 + i)
-        return torch.randn(ext[i].num_nodes * ns[i], 3, generator=g)
+        return initial_positions(i, ext[i].num_nodes * ns[i], seed)
 
     def run(group: List[int], clip_local):
         """one sampler call on the conformers of ``group`` -> list of per-molecule tensors"""
@@ -98,11 +107,14 @@ def sample_conformers(model, mols: Sequence[Molecule], num_samples: Union[int, S
         z, bi, bt, b = torch.cat(zs), torch.cat(bis, 1), torch.cat(bts), torch.cat(bs)
         pos0 = torch.cat([pos_init_of(i) for i in group])
         gid = torch.cat([torch.arange(gid0[i], gid0[i + 1]) for i in group])
+        extra = {}
+        if noise_fn is not None:
+            extra["noise"] = torch.cat([noise_fn(i, ext[i].num_nodes * ns[i]) for i in group], dim=1)
         pos, traj = model.langevin_dynamics_sample_diffusion(
             atom_type=z.to(device), pos_init=pos0.to(device), bond_index=bi.to(device), bond_type=bt.to(device),
             batch=b.to(device), num_graphs=g, extend_order=False, n_steps=n_steps, step_lr=step_lr, w_global=w_global,
             global_start_sigma=global_start_sigma, clip=clip, clip_local=clip_local, sampling_type=sampling_type, eta=eta,
-            seed=seed, mol_gid=gid.to(device), return_traj=save_traj)
+            seed=seed, mol_gid=gid.to(device), return_traj=save_traj, **extra)
         full = torch.stack(list(traj)) if save_traj else pos.cpu()
         out, a = [], 0
         for i in group:
@@ -121,9 +133,24 @@ def sample_conformers(model, mols: Sequence[Molecule], num_samples: Union[int, S
             for i, t in zip(group, run(group, None)):
                 finish(i, t, None)
             return
-        except FloatingPointError:
-            pass
+        except FloatingPointError as err:
+            bad_graphs = getattr(err, "bad_graphs", None)
         if len(group) > 1:                                   # isolate the molecule(s) that produced NaN
+            if bad_graphs:
+                # the sampler reports which conformers went NaN (agd_nan_steps): the others are repeated together without
+                # them - one more call instead of a bisection - and only the offenders take the retry path one by one
+                first, bad = 0, set()
+                for i in group:
+                    if any(first <= g < first + ns[i] for g in bad_graphs):
+                        bad.add(i)
+                    first += ns[i]
+                good = [i for i in group if i not in bad]
+                if bad and good:
+                    solve(good)
+                    for i in group:
+                        if i in bad:
+                            solve([i])
+                    return
             mid = len(group) // 2
             solve(group[:mid])
             solve(group[mid:])
@@ -138,6 +165,40 @@ def sample_conformers(model, mols: Sequence[Molecule], num_samples: Union[int, S
     for batch in plan_batches(sizes, [ns[i] for i in todo], max_atoms_per_call):
         solve([todo[k] for k in batch])
     return results
+
+
+def repeat_data(data, num_repeat: int):
+    """``repeat_data`` of the reference (utils/misc.py:88-90: ``Batch.from_data_list([data.clone()] * n)``) for any object
+    that carries ``atom_type (n,)``, ``edge_index (2, e)`` and ``edge_type (e,)`` - a PyG ``Data`` or a plain namespace.
+    Returns a namespace with the ``Batch`` fields the sampler call reads (scripts/test.py:147-164): ``atom_type, edge_index,
+    edge_type, batch, num_graphs, num_nodes``."""
+    from types import SimpleNamespace
+    z, ei, et = data.atom_type, data.edge_index, data.edge_type
+    n = int(z.numel())
+    offs = torch.arange(num_repeat, device=ei.device).repeat_interleave(ei.size(1)) * n
+    return SimpleNamespace(atom_type=z.repeat(num_repeat), edge_index=ei.repeat(1, num_repeat) + offs, edge_type=et.repeat(num_repeat),
+                           batch=torch.arange(num_repeat, device=z.device).repeat_interleave(n), num_graphs=num_repeat,
+                           num_nodes=n * num_repeat)
+
+
+def molecules_from_batch(batch) -> List[Molecule]:
+    """The graphs of a PyG-style ``Batch`` / ``Data`` (``atom_type, edge_index, edge_type[, batch]``; bond graph directed both
+    ways and, as the datasets store it, possibly already order-extended) as ``Molecule`` records for ``sample_conformers``."""
+    z = batch.atom_type.cpu()
+    ei, et = batch.edge_index.cpu(), batch.edge_type.cpu()
+    b = getattr(batch, "batch", None)
+    b = torch.zeros(z.numel(), dtype=torch.long) if b is None else b.cpu()
+    out = []
+    counts = torch.bincount(b, minlength=int(b.max()) + 1 if b.numel() else 0)
+    starts = torch.cumsum(counts, 0) - counts
+    eb = b[ei[0]] if ei.numel() else torch.zeros(0, dtype=torch.long)
+    for g in range(counts.numel()):
+        a0, n = int(starts[g]), int(counts[g])
+        m = eb == g
+        e, t = ei[:, m] - a0, et[m]
+        order = torch.argsort(e[0] * n + e[1])               # Molecule keeps its bond list sorted by row * n + col
+        out.append(Molecule(z[a0:a0 + n].numpy().astype("int64"), e[:, order].numpy().astype("int64"), t[order].numpy().astype("int64")))
+    return out
 
 
 def estimated_cost(mols: Sequence[Molecule], num_samples: int = 2) -> int:

@@ -160,6 +160,11 @@ int agd_forward_edges(agd_handle* h, agd_batch* b, const float* pos_dev, const a
  * the call returns AGD_ERR_NAN in that case (the host mirror raises FloatingPointError). */
 int agd_sample(agd_handle* h, agd_batch* b, float* pos_dev_inout, const agd_sample_params* p,
                int32_t* first_nan_step, void* stream);
+/* After agd_sample: for every molecule of the batch the first step at which its positions became NaN, or -1 (host array of
+ * n_mols entries).  Lets a caller that batches many molecules per call repeat only the offenders (the reference's retry loop,
+ * scripts/test.py:144-181, is per molecule).  agd_sample itself stops launching steps soon after the first NaN (it polls the
+ * device flag every 32 launches) and returns AGD_ERR_NAN. */
+int agd_nan_steps(agd_batch* b, int32_t* host_out, int32_t n_mols);
 
 /* _extend_graph_order / AddHigherOrderEdges (common.py:135-205) on device for one batch:
  * CSR bond graph in, per-atom sorted (dst, type) lists out; two passes (count, fill). */

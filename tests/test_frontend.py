@@ -99,3 +99,47 @@ def test_resume_num_samples_and_traj():
     for i, r in enumerate(out):
         if r is not None:
             assert r.num_samples == 1 + i % 3 and r.pos_gen.shape == (4, r.num_samples * mols[i].num_nodes, 3)
+
+
+def test_repeat_data_and_batch_round_trip():
+    """repeat_data (utils/misc.py:88-90) on a duck-typed Data, and PyG-style Batch -> Molecule records -> the same collate"""
+    from agdiff_b200 import graph
+    mols = [graph.extend_bond_order_host(m) for m in synth.qm9_like(3, seed=8)]
+    z, bi, bt, b, G = graph.collate([mols[1]], 3)
+    data = SimpleNamespace(atom_type=torch.as_tensor(mols[1].atom_type), edge_index=torch.as_tensor(mols[1].bond_index),
+                           edge_type=torch.as_tensor(mols[1].bond_type))
+    rep = frontend.repeat_data(data, 3)
+    assert rep.num_graphs == 3 and rep.num_nodes == z.numel()
+    assert torch.equal(rep.atom_type, z) and torch.equal(rep.edge_index, bi) and torch.equal(rep.edge_type, bt) and torch.equal(rep.batch, b)
+    z, bi, bt, b, G = graph.collate(mols, 1)
+    perm = torch.randperm(bi.size(1), generator=torch.Generator().manual_seed(0))       # a Batch need not be sorted
+    back = frontend.molecules_from_batch(SimpleNamespace(atom_type=z, edge_index=bi[:, perm], edge_type=bt[perm], batch=b))
+    assert len(back) == len(mols)
+    for a, m in zip(back, mols):
+        assert np.array_equal(a.atom_type, m.atom_type) and np.array_equal(a.bond_index, m.bond_index) and np.array_equal(a.bond_type, m.bond_type)
+
+
+def test_nan_report_avoids_the_bisection():
+    """when the sampler says WHICH conformers went NaN (FloatingPointError.bad_graphs), the good molecules are repeated in one
+    call and only the offenders are retried with clip_local - no bisection"""
+    mols = _mols()
+    bad_size = mols[2].num_nodes
+
+    class Reporting(MockModel):
+        def langevin_dynamics_sample_diffusion(self, atom_type, pos_init, bond_index, bond_type, batch, num_graphs, extend_order,
+                                               n_steps=5000, clip_local=None, **kw):
+            counts = torch.bincount(batch, minlength=num_graphs).tolist()
+            if clip_local is None and bad_size in counts:
+                self.calls.append((counts, clip_local))
+                err = FloatingPointError()
+                err.bad_graphs = [g for g, c in enumerate(counts) if c == bad_size]
+                raise err
+            return super().langevin_dynamics_sample_diffusion(atom_type, pos_init, bond_index, bond_type, batch, num_graphs,
+                                                              extend_order, n_steps=n_steps, clip_local=clip_local, **kw)
+    m = Reporting()
+    out = frontend.sample_conformers(m, mols, 2, n_steps=2, max_atoms_per_call=10 ** 9)
+    n_bad = sum(1 for x in mols if x.num_nodes == bad_size)
+    # 1 failed call with everything, 1 call with the good ones, then per offender: 1 failing unclipped call + 1 clipped
+    assert len(m.calls) == 2 + 2 * n_bad
+    for i, r in enumerate(out):
+        assert r.clip_local == (20.0 if mols[i].num_nodes == bad_size else None) and not r.failed

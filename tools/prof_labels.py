@@ -13,9 +13,10 @@ from agdiff_b200 import _lib, graph, synth
 from bench import CFG
 
 n_mols = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+kind = sys.argv[2] if len(sys.argv) > 2 else "drugs"
 torch.manual_seed(2021)
 m = agdiff_b200.get_model(SimpleNamespace(**CFG)).eval().to("cuda:0")
-mols = [graph.extend_bond_order_host(x) for x in synth.drugs_like(n_mols, seed=2021)]
+mols = [graph.extend_bond_order_host(x) for x in (synth.drugs_like(n_mols, seed=2021) if kind == "drugs" else synth.qm9_like(n_mols, seed=2021))]
 z, bi, bt, b, G = graph.collate(mols, 2)
 pos = (torch.randn(z.numel(), 3, generator=torch.Generator().manual_seed(0)) * 1.5).to("cuda:0")
 m._sync_weights()
