@@ -2,15 +2,17 @@
 // eq_transform of the local and (when sigma < global_start_sigma) global edge scores
 // (geometry.py:9-17), clip_norm (dualenc.py:586-589), the noise/position update, the NaN guard,
 // center_pos (dualenc.py:581-583) and the optional clamp.  One CTA per molecule; each atom sums
-// its CSC in-edge segment and its canonical out-edge segment, so there are no atomics and the
-// result is bit-reproducible (and independent of how molecules are sharded over GPUs).
+// its CSC in-edge segments and its canonical out-edge segments (four threads, one per segment), so
+// there are no atomics and the result is bit-reproducible (and independent of how molecules are
+// sharded over GPUs).
 #include "common.cuh"
 #include "kernels.h"
 
 namespace agd {
 
-constexpr int STEP_THREADS = 64;
-constexpr int STEP_MAX_PER_THREAD = AGD_MAX_MOL_ATOMS / STEP_THREADS;
+constexpr int STEP_THREADS = 256;                 // four threads per atom
+constexpr int STEP_ATOMS = STEP_THREADS / 4;      // atoms per sweep of the CTA
+constexpr int STEP_MAX_PER_THREAD = AGD_MAX_MOL_ATOMS / STEP_ATOMS;
 
 __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -69,62 +71,80 @@ __device__ __forceinline__ void clip3(float& x, float& y, float& z, float limit)
   }
 }
 
+// One CTA per molecule, FOUR threads per atom: lane part p of an atom's quad sums one of its four edge segments (local in,
+// local out, global in, global out; each in CSC / canonical order), the quad combines them in a fixed order with shuffles -
+// eq = (in + out) per branch - so the result is bit-reproducible and does not depend on batch composition, while the four
+// dependent-load chains of an atom run side by side (the one-thread-per-atom version was latency-bound at 6 % issue rate).
 __global__ void __launch_bounds__(STEP_THREADS) langevin_step_kernel(const StepArgs a) {
   __shared__ float red[3][STEP_THREADS / 32];
+  __shared__ int s_bad;
   const int m = blockIdx.x;
   const int a0 = a.mol_ptr[m], n = a.mol_ptr[m + 1] - a0;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, part = tid & 3, slot = tid >> 2;
   const int step = a.counters[1];
   const float sigma = a.sched[4 * step], step_size = a.sched[4 * step + 1], nscale = a.sched[4 * step + 2];
   const float* pos = a.pos;
+  if (tid == 0) s_bad = 0;
   float nx[STEP_MAX_PER_THREAD], ny[STEP_MAX_PER_THREAD], nz[STEP_MAX_PER_THREAD];
   float sx = 0.f, sy = 0.f, sz = 0.f;
   bool bad = false;
 #pragma unroll
   for (int q = 0; q < STEP_MAX_PER_THREAD; ++q) {
-    const int i = tid + q * STEP_THREADS;
+    const int i = slot + q * STEP_ATOMS;
     nx[q] = ny[q] = nz[q] = 0.f;
-    if (i >= n) continue;
-    const int at = a0 + i;
+    const bool active = i < n;                       // (whole quads are active or not: shuffles below stay converged per quad)
+    const int at = a0 + (active ? i : 0);
     const float px = pos[3 * (size_t)at], py = pos[3 * (size_t)at + 1], pz = pos[3 * (size_t)at + 2];
-    // ---- local: eq_transform(edge_inv_local, pos, local edges)
-    float lx = 0.f, ly = 0.f, lz = 0.f;
-    for (int e = a.lin_ptr[at]; e < a.lin_ptr[at + 1]; ++e) {       // atom is edge_index[1]: subtract
-      const int s = a.lsrc[e];
-      const float inv = 1.0f / a.llen[e], sc = a.sl_csc[e];
-      lx -= (inv * (pos[3 * (size_t)s] - px)) * sc;
-      ly -= (inv * (pos[3 * (size_t)s + 1] - py)) * sc;
-      lz -= (inv * (pos[3 * (size_t)s + 2] - pz)) * sc;
+    float vx = 0.f, vy = 0.f, vz = 0.f;
+    if (active) {
+      if (part == 0) {          // local, atom is edge_index[1]: subtract
+        for (int e = a.lin_ptr[at]; e < a.lin_ptr[at + 1]; ++e) {
+          const int s = a.lsrc[e];
+          const float inv = 1.0f / a.llen[e], sc = a.sl_csc[e];
+          vx -= (inv * (pos[3 * (size_t)s] - px)) * sc;
+          vy -= (inv * (pos[3 * (size_t)s + 1] - py)) * sc;
+          vz -= (inv * (pos[3 * (size_t)s + 2] - pz)) * sc;
+        }
+      } else if (part == 1) {   // local, atom is edge_index[0]: add
+        for (int c = a.lout_ptr[at]; c < a.lout_ptr[at + 1]; ++c) {
+          const int t = a.lcdst[c];
+          const float inv = 1.0f / a.lclen[c], sc = a.sl_canon[c];
+          vx += (inv * (px - pos[3 * (size_t)t])) * sc;
+          vy += (inv * (py - pos[3 * (size_t)t + 1])) * sc;
+          vz += (inv * (pz - pos[3 * (size_t)t + 2])) * sc;
+        }
+      } else if (a.p.use_global) {
+        if (part == 2) {        // global: edge_inv_global * (1 - local_mask), in-edges
+          for (int e = a.in_ptr[at]; e < a.in_ptr[at + 1]; ++e) {
+            if (a.e_type[e] > 0) continue;
+            const int s = a.e_src[e];
+            const float inv = 1.0f / a.e_len[e], sc = a.s_csc[e];
+            vx -= (inv * (pos[3 * (size_t)s] - px)) * sc;
+            vy -= (inv * (pos[3 * (size_t)s + 1] - py)) * sc;
+            vz -= (inv * (pos[3 * (size_t)s + 2] - pz)) * sc;
+          }
+        } else {                // global, out-edges
+          for (int c = a.out_ptr[at]; c < a.out_ptr[at + 1]; ++c) {
+            if (a.c_type[c] > 0) continue;
+            const int t = a.c_dst[c];
+            const float inv = 1.0f / a.c_len[c], sc = a.s_canon[c];
+            vx += (inv * (px - pos[3 * (size_t)t])) * sc;
+            vy += (inv * (py - pos[3 * (size_t)t + 1])) * sc;
+            vz += (inv * (pz - pos[3 * (size_t)t + 2])) * sc;
+          }
+        }
+      }
     }
-    for (int c = a.lout_ptr[at]; c < a.lout_ptr[at + 1]; ++c) {     // atom is edge_index[0]: add
-      const int t = a.lcdst[c];
-      const float inv = 1.0f / a.lclen[c], sc = a.sl_canon[c];
-      lx += (inv * (px - pos[3 * (size_t)t])) * sc;
-      ly += (inv * (py - pos[3 * (size_t)t + 1])) * sc;
-      lz += (inv * (pz - pos[3 * (size_t)t + 2])) * sc;
-    }
+    // quad combine: parts (0,1) -> local sum, parts (2,3) -> global sum; every lane of the quad ends up with both
+    const float ox = __shfl_xor_sync(0xffffffffu, vx, 1), oy = __shfl_xor_sync(0xffffffffu, vy, 1), oz = __shfl_xor_sync(0xffffffffu, vz, 1);
+    const float bx = (part & 1) ? ox + vx : vx + ox, by = (part & 1) ? oy + vy : vy + oy, bz = (part & 1) ? oz + vz : vz + oz;   // in + out
+    const float qx = __shfl_xor_sync(0xffffffffu, bx, 2), qy = __shfl_xor_sync(0xffffffffu, by, 2), qz = __shfl_xor_sync(0xffffffffu, bz, 2);
+    float lx = (part & 2) ? qx : bx, ly = (part & 2) ? qy : by, lz = (part & 2) ? qz : bz;
+    float gx = (part & 2) ? bx : qx, gy = (part & 2) ? by : qy, gz = (part & 2) ? bz : qz;
+    if (!active || part != 0) continue;              // lane 0 of the quad finishes the atom
     if (a.p.clip_local >= 0.f) clip3(lx, ly, lz, a.p.clip_local);
-    // ---- global: edge_inv_global * (1 - local_mask), eq_transform, clip_norm
-    float gx = 0.f, gy = 0.f, gz = 0.f;
-    if (a.p.use_global) {
-      for (int e = a.in_ptr[at]; e < a.in_ptr[at + 1]; ++e) {
-        if (a.e_type[e] > 0) continue;
-        const int s = a.e_src[e];
-        const float inv = 1.0f / a.e_len[e], sc = a.s_csc[e];
-        gx -= (inv * (pos[3 * (size_t)s] - px)) * sc;
-        gy -= (inv * (pos[3 * (size_t)s + 1] - py)) * sc;
-        gz -= (inv * (pos[3 * (size_t)s + 2] - pz)) * sc;
-      }
-      for (int c = a.out_ptr[at]; c < a.out_ptr[at + 1]; ++c) {
-        if (a.c_type[c] > 0) continue;
-        const int t = a.c_dst[c];
-        const float inv = 1.0f / a.c_len[c], sc = a.s_canon[c];
-        gx += (inv * (px - pos[3 * (size_t)t])) * sc;
-        gy += (inv * (py - pos[3 * (size_t)t + 1])) * sc;
-        gz += (inv * (pz - pos[3 * (size_t)t + 2])) * sc;
-      }
-      clip3(gx, gy, gz, a.p.clip);
-    }
+    if (a.p.use_global) clip3(gx, gy, gz, a.p.clip);
+    else gx = gy = gz = 0.f;
     const float ex = lx + gx * a.p.w_global, ey = ly + gy * a.p.w_global, ez = lz + gz * a.p.w_global;
     float z0, z1, z2;
     if (a.p.noise) {
@@ -157,9 +177,10 @@ __global__ void __launch_bounds__(STEP_THREADS) langevin_step_kernel(const StepA
   for (int w = 0; w < STEP_THREADS / 32; ++w) { cx += red[0][w]; cy += red[1][w]; cz += red[2][w]; }
   const float cnt = (float)(n > 0 ? n : 1);
   cx /= cnt; cy /= cnt; cz /= cnt;
+  if (part != 0) return;
 #pragma unroll
   for (int q = 0; q < STEP_MAX_PER_THREAD; ++q) {
-    const int i = tid + q * STEP_THREADS;
+    const int i = slot + q * STEP_ATOMS;
     if (i >= n) continue;
     const int at = a0 + i;
     float x = nx[q] - cx, y = ny[q] - cy, z = nz[q] - cz;
