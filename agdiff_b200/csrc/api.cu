@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -61,6 +63,7 @@ struct agd_handle {
   int f16_node = 1;
   int f16_debug_filt = 0;
   unsigned long long* f16_timing = nullptr;
+  int mlp_act = 0;  // AGD_ACT_* of the pair MLPs (agd_set_option "mlp_act")
   int use_tc = 2;   // AGD_TC_FILTERS / agd_set_mode: 0 FFMA, 1 tcgen05 3xTF32, 2 tcgen05 + 3xFP16 filter kernels
 };
 
@@ -145,11 +148,14 @@ static LaunchCtx make_ctx(agd_handle* h) {
   c.num_sms = h->num_sms;
   c.launch_counter = &h->launches;
   c.prof = nullptr;
-  c.use_tc = h->use_tc;
+  // mlp_act != relu: the pair MLPs run on the fp32 FFMA kernel, which reads the fp32 encoder state - written by the 3xTF32 /
+  // FFMA encoders only - so the fp16-split mode is not used for such a model
+  c.mlp_act = h->mlp_act;
+  c.use_tc = (h->mlp_act != 0 && h->use_tc == 2) ? 1 : h->use_tc;
   c.f16_fuse = h->f16_fuse;
-  c.f16_mlp = (h->use_tc == 2) ? h->f16_mlp : 0;
-  c.f16_pair = (h->use_tc == 2) ? h->f16_pair : 0;
-  c.f16_node = (h->use_tc == 2) ? h->f16_node : 0;
+  c.f16_mlp = (c.use_tc == 2) ? h->f16_mlp : 0;
+  c.f16_pair = (c.use_tc == 2) ? h->f16_pair : 0;
+  c.f16_node = (c.use_tc == 2) ? h->f16_node : 0;
   c.f16_debug_filt = h->f16_debug_filt;
   c.f16_timing = h->f16_timing;
   c.cutoff = h->cfg.cutoff;
@@ -173,44 +179,70 @@ static int leave(agd_handle* h, void* user_stream) {
   return AGD_OK;
 }
 
+// NVTX range per phase of a network evaluation (host side: visible in Nsight Systems timelines around the launches; inside a
+// captured graph they bracket the capture, not the replays)
+struct Nvtx {
+  explicit Nvtx(const char* name) { nvtxRangePushA(name); }
+  ~Nvtx() { nvtxRangePop(); }
+};
+
 // ------------------------------------------------------------------ launch sequences
 static void run_local_branch(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos, const float** h_out) {
+  Nvtx r_all("agd.local_branch");
+  {
+  Nvtx r("agd.edge_encoder.local");
   if (c.f16_mlp) launch_encoder_local_f16(c, b, w, pos);
   else if (c.use_tc) launch_encoder_local_tc(c, b, w, pos);
   else launch_encoder_local(c, b, w, pos);
-  launch_gin_embed(c, b, w);
+  }
   const float* x_in = b.gx0;
   float* x_out = b.gx1;
-  for (int k = 0; k < c.num_convs_local; ++k) {
-    if (c.use_tc) launch_gin_layer_tc(c, b, w, k, x_in, x_out); else launch_gin_layer(c, b, w, k, x_in, x_out);
-    const float* t = x_in;
-    x_in = x_out;
-    x_out = const_cast<float*>(t);
+  {
+    Nvtx r("agd.gin");
+    launch_gin_embed(c, b, w);
+    for (int k = 0; k < c.num_convs_local; ++k) {
+      if (c.use_tc) launch_gin_layer_tc(c, b, w, k, x_in, x_out); else launch_gin_layer(c, b, w, k, x_in, x_out);
+      const float* t = x_in;
+      x_in = x_out;
+      x_out = const_cast<float*>(t);
+    }
   }
+  Nvtx r_pair("agd.pair_mlp.local");
   if (c.f16_pair) launch_pair_local_f16(c, b, w, x_in);
-  else if (c.use_tc) launch_pair_local_tc(c, b, w, x_in);
+  else if (c.use_tc && c.mlp_act == 0) launch_pair_local_tc(c, b, w, x_in);
   else launch_pair_local(c, b, w, x_in);
   if (h_out) *h_out = x_in;
 }
 
 static void run_global_branch(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos, bool build = true) {
-  if (build) launch_build_edges(c, b, pos);
-  if (c.f16_mlp) launch_encoder_global_f16(c, b, w);
-  else if (c.use_tc) launch_encoder_global_tc(c, b, w);
-  else launch_encoder_global(c, b, w);
+  Nvtx r_all("agd.global_branch");
+  if (build) {
+    Nvtx r("agd.edges");
+    launch_build_edges(c, b, pos);
+  }
+  {
+    Nvtx r("agd.edge_encoder.global");
+    if (c.f16_mlp) launch_encoder_global_f16(c, b, w);
+    else if (c.use_tc) launch_encoder_global_tc(c, b, w);
+    else launch_encoder_global(c, b, w);
+  }
+  nvtxRangePushA("agd.schnet");
   if (c.use_tc == 2) launch_edge_weights_f16(c, b, w);
   if (c.f16_node) launch_schnet_node_f16(c, b, w, -1);
   else if (c.use_tc) launch_schnet_node_tc(c, b, w, -1);
   else launch_schnet_node(c, b, w, -1);
   for (int k = 0; k < c.num_convs; ++k) {
+    Nvtx r_blk("agd.schnet.block");
     launch_filters(c, b, w, k);
     if (!((c.use_tc == 1 && filters_tc_fused()) || (c.use_tc == 2 && c.f16_fuse))) launch_aggregate(c, b.xcat, b.filt, b.e_src, b.in_ptr, b.n_atoms, 192, b.agg);
     if (c.f16_node) launch_schnet_node_f16(c, b, w, k);
     else if (c.use_tc) launch_schnet_node_tc(c, b, w, k);
     else launch_schnet_node(c, b, w, k);
   }
+  nvtxRangePop();   // agd.schnet
+  Nvtx r_pair("agd.pair_mlp.global");
   if (c.f16_pair) launch_pair_global_f16(c, b, w);
-  else if (c.use_tc) launch_pair_global_tc(c, b, w);
+  else if (c.use_tc && c.mlp_act == 0) launch_pair_global_tc(c, b, w);
   else launch_pair_global(c, b, w);
 }
 
@@ -557,6 +589,7 @@ int agd_sample(agd_handle* h, agd_batch* b, float* pos, const agd_sample_params*
     if (use_global) run_global_branch(c, d, h->w, pos);
     run_local_branch(c, d, h->w, pos, nullptr);
     sp.use_global = use_global ? 1 : 0;
+    Nvtx r("agd.langevin_step");
     launch_step(c, d, pos, sp);
     launch_advance(c, d);
   };
@@ -704,6 +737,7 @@ int agd_op_cfconv_aggregate(const float* x, const float* W, const int32_t* src, 
   c.f16_node = 0;
   c.f16_debug_filt = 0;
   c.f16_timing = nullptr;
+  c.mlp_act = 0;
   launch_aggregate(c, x, W, src, in_ptr, n_nodes, F, out);
   CUDA_TRY(cudaGetLastError());
   return AGD_OK;
@@ -756,6 +790,10 @@ int agd_set_option(agd_handle* h, const char* name, int value) {
   else if (std::strcmp(name, "f16_mlp") == 0) h->f16_mlp = value ? 1 : 0;
   else if (std::strcmp(name, "f16_pair") == 0) h->f16_pair = value ? 1 : 0;
   else if (std::strcmp(name, "f16_node") == 0) h->f16_node = value ? 1 : 0;
+  else if (std::strcmp(name, "mlp_act") == 0) {
+    if (value < 0 || value >= AGD_ACT_COUNT) return fail(AGD_ERR_INVALID, "unknown mlp_act id");
+    h->mlp_act = value;
+  }
   else if (std::strcmp(name, "f16_debug_filt") == 0) h->f16_debug_filt = value;   // bit 0: write filt; bits 1.. : timing experiments (tc_cfconv.cu)
   else if (std::strcmp(name, "f16_timing") == 0) {   // diagnostics: 1 = allocate + zero the phase counters, 0 = off
     if (value && !h->f16_timing) {

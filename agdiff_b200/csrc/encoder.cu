@@ -105,7 +105,22 @@ struct PairArgs {
   const float* feat;    // g2 (global) / edge_attr (local) [rows][128]
   const int *src, *dst, *canon;
   float *s_csc, *s_canon;
+  int act;              // mlp_act (common.py:44-84 takes any torch.nn.functional name): AGD_ACT_* of kernels.h
 };
+
+// mlp_act of the pair MLPs (MultiLayerPerceptron, common.py:59-62: getattr(F, activation)), torch's fp32 definitions
+__device__ __forceinline__ float pair_act(float x, int act) {
+  switch (act) {
+    case AGD_ACT_GELU: return gelu_erf(x);
+    case AGD_ACT_SILU: return x / (1.0f + expf(-x));
+    case AGD_ACT_TANH: return tanhf(x);
+    case AGD_ACT_SIGMOID: return sigmoidf_(x);
+    case AGD_ACT_LEAKY_RELU: return x > 0.f ? x : 0.01f * x;
+    case AGD_ACT_ELU: return x > 0.f ? x : expm1f(x);
+    case AGD_ACT_SOFTPLUS: return x > 20.0f ? x : log1pf(expf(x));
+    default: return relu_(x);
+  }
+}
 
 // edge_inv = MLP([h[row]*h[col], edge_attr]); first Linear split in two K=128 passes so one
 // activation tile suffices (2 CTAs/SM).
@@ -134,7 +149,7 @@ __global__ void __launch_bounds__(NT, 2) pair_mlp_kernel(const PairArgs a) {
     tile_gemm<HID, HID, false>(a.w.P1h, As, Ws, acc, tc.tx, tc.ty);
     tile_load_T<HID>(a.feat, row0, n_rows, HID, 0, As);
     tile_gemm<HID, HID, true>(a.w.P1e, As, Ws, acc, tc.tx, tc.ty);
-    tile_store_smem<HID>(acc, As, tc.tx, tc.ty, [&](float v, int m, int n) { return relu_(v + __ldg(a.w.p1b + n)); });
+    tile_store_smem<HID>(acc, As, tc.tx, tc.ty, [&](float v, int m, int n) { return pair_act(v + __ldg(a.w.p1b + n), a.act); });
     float acc2[8][4];
     tile_gemm<HID, 64, false>(a.w.P2, As, Ws, acc2, tc.tx, tc.ty);
     // last Linear (64 -> 1): per-thread partial over its 4 columns, reduce over the 16 tx threads
@@ -146,7 +161,7 @@ __global__ void __launch_bounds__(NT, 2) pair_mlp_kernel(const PairArgs a) {
       const int n = tc.tx * 4 + j;
       const float wj = __ldg(a.w.p3w + n), bj = __ldg(a.w.p2b + n);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) part[i] = fmaf(relu_(acc2[i][j] + bj), wj, part[i]);
+      for (int i = 0; i < 8; ++i) part[i] = fmaf(pair_act(acc2[i][j] + bj, a.act), wj, part[i]);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -219,6 +234,7 @@ void launch_pair_global(const LaunchCtx& c, const BatchDev& b, const ModelW& w) 
   a.canon = b.e_canon;
   a.s_csc = b.s_csc;
   a.s_canon = b.s_canon;
+  a.act = c.mlp_act;
   pair_mlp_kernel<<<tiles_grid(b.cap, c.num_sms, 2), NT, PAIR_SMEM, c.stream>>>(a);
   note_launch(c, "pair.global");
 }
@@ -236,6 +252,7 @@ void launch_pair_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w, c
   a.canon = b.lc_canon;
   a.s_csc = b.sl_csc;
   a.s_canon = b.sl_canon;
+  a.act = c.mlp_act;
   pair_mlp_kernel<<<tiles_grid(b.n_local, c.num_sms, 2), NT, PAIR_SMEM, c.stream>>>(a);
   note_launch(c, "pair.local");
 }

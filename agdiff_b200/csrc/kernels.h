@@ -9,6 +9,7 @@
 
 namespace agd {
 
+enum { AGD_ACT_RELU = 0, AGD_ACT_GELU, AGD_ACT_SILU, AGD_ACT_TANH, AGD_ACT_SIGMOID, AGD_ACT_LEAKY_RELU, AGD_ACT_ELU, AGD_ACT_SOFTPLUS, AGD_ACT_COUNT };
 constexpr int MAX_BLOCKS = 8;   // SchNet interaction blocks supported (reference config: 6)
 constexpr int MAX_GIN = 8;      // GIN layers supported (reference config: 4)
 
@@ -130,6 +131,7 @@ struct LaunchCtx {
   int f16_pair;    // use_tc == 2: pair MLPs on the fp16 two-slot kernels
   int f16_node;    // use_tc == 2: SchNet node chain on the fp16 kernel with double-buffered weight streaming (tc_node16.cu)
   int f16_fuse;    // use_tc == 2: both CFConv layers of a block + the aggregation in one launch (tc_cfconv.cu; no filt tensor, no aggregate kernel)
+  int mlp_act;     // activation of the pair MLPs (AGD_ACT_*); anything but relu runs them on the fp32 FFMA kernel
   float cutoff;
   int smooth;
   int num_convs, num_convs_local;

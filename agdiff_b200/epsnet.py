@@ -35,6 +35,9 @@ from . import _lib
 from .pack import fold_state_dict, pack
 
 NUM_BOND_TYPES = 22  # len(BOND_TYPES), reference src/agdiff/utils/chem.py:17
+# mlp_act (reference common.py:59-62: getattr(F, activation)) -> agd_set_option("mlp_act", id).  relu (every shipped config) runs
+# on the fp16-split tensor-core kernels, the others on the fp32 FFMA pair kernel.
+MLP_ACTS = ("relu", "gelu", "silu", "tanh", "sigmoid", "leaky_relu", "elu", "softplus")
 
 
 # --------------------------------------------------------------------------------------------
@@ -304,8 +307,8 @@ class DualEncoderEpsNetwork(nn.Module):
         self.num_timesteps = self.betas.size(0)
         if H != 128:
             raise NotImplementedError("hidden_dim is pinned to 128 (reference schnet.py:190-192)")
-        if getattr(config, "mlp_act", "relu") != "relu":
-            raise NotImplementedError("mlp_act=%r: the kernels implement the shipped configs' relu" % config.mlp_act)
+        if getattr(config, "mlp_act", "relu") not in MLP_ACTS:
+            raise NotImplementedError("mlp_act=%r: supported are %s" % (config.mlp_act, ", ".join(MLP_ACTS)))
         self._handle = None
         self._handle_device = None
         self._packed_version = None
@@ -328,6 +331,7 @@ class DualEncoderEpsNetwork(nn.Module):
             h = C.c_void_p()
             _lib.check(lib.agd_create(C.byref(cfg), C.byref(h)))
             self._handle, self._handle_device, self._packed_version = h, dev, None
+            _lib.check(lib.agd_set_option(h, b"mlp_act", MLP_ACTS.index(getattr(self.config, "mlp_act", "relu"))))
         return self._handle
 
     def _release(self):

@@ -210,6 +210,10 @@ int agd_get_mode(const agd_handle* h);
  *   "f16_mlp"   (env AGD_F16_MLP)   edge encoder on the fp16 two-slot kernels (0: 3xTF32 kernels)
  *   "f16_pair"  (env AGD_F16_PAIR)  pair MLPs on the fp16 two-slot kernels
  *   "f16_node"  (env AGD_F16_NODE)  SchNet node chain on the fp16 kernel with double-buffered weight streaming
+ *   "mlp_act"   activation of the two pair MLPs (config field mlp_act; common.py:59-62 takes any torch.nn.functional name):
+ *               0 relu (default), 1 gelu, 2 silu, 3 tanh, 4 sigmoid, 5 leaky_relu, 6 elu, 7 softplus.  Anything but relu runs the
+ *               pair MLPs on the fp32 FFMA kernel and the encoders on the 3xTF32 kernels (the fp16-split pair kernel relies on
+ *               relu being positively homogeneous)
  *   "f16_debug_filt" (0)  the fused CFConv kernels also write the filter tensor (tests)
  *   "f16_timing"     (0)  clock64 phase counters of the CFConv kernels (needs a build with -DAGD_F16_TIMING), agd_debug_timing */
 int agd_set_option(agd_handle* h, const char* name, int value);

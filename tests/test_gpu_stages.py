@@ -314,3 +314,24 @@ def test_default_seed_is_fresh_per_call_and_reproducible():
     torch.manual_seed(77)
     p3, _ = m.langevin_dynamics_sample_diffusion(*args, **kw)
     assert not torch.equal(p1, p2) and torch.equal(p1, p3)
+
+
+@pytest.mark.parametrize("act", ["gelu", "silu", "tanh", "leaky_relu", "softplus"])
+def test_pair_mlp_activations_other_than_relu(act):
+    """config field mlp_act (common.py:44-84 takes any torch.nn.functional name): forward against the oracle"""
+    cfg = dict(CONFIGS["drugs"], mlp_act=act)
+    torch.manual_seed(2021)
+    m = agdiff_b200.get_model(SimpleNamespace(**cfg)).eval()
+    m.load_state_dict(O.perturb_state_dict(m.state_dict(), seed=4), strict=False)
+    sd = state_dict_cpu(m)
+    m = m.to(DEV)
+    mols = [graph.extend_bond_order_host(x) for x in synth.drugs_like(5, seed=9, force_max=False)]
+    z, bi, bt, b, G = graph.collate(mols, 1)
+    pos = torch.randn(z.numel(), 3, generator=torch.Generator().manual_seed(2)) * 2.0
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, z, pos, bi, bt, b, extend_order=False)
+    out = m(z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), None, return_edges=True, extend_order=False)
+    assert torch.equal(out[2].cpu(), ref[2])
+    ng, nl = fp32_noise(sd, cfg, z, pos, bi, bt, b, ref)
+    assert_close(out[0], ref[0], what="edge_inv_global (%s)" % act, extra_atol=4 * ng)
+    assert_close(out[1], ref[1], what="edge_inv_local (%s)" % act, extra_atol=4 * nl)
