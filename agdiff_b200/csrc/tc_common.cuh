@@ -97,6 +97,14 @@ constexpr int COL_D = 0, COL_AHI = 128, COL_ALO = 256, COL_D2 = 384, TMEM_COLS =
 }  // namespace tc
 
 
+// 1 / (1 + e^-x) on the SFU: ex2.approx + rcp.approx (relative error ~3e-7; e^-x -> inf gives exactly 0, NaN propagates)
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+
 // softplus(beta*x) - ln2 on the SFU: ex2.approx / lg2.approx (absolute error ~4e-7; the parity bar is 1e-4 and the
 // value feeds a 128-term fp32 dot product).  Matches F.softplus' threshold-20 branch.
 __device__ __forceinline__ float ssp_fast(float x, float beta) {

@@ -340,7 +340,19 @@ struct TcGinArgs {
   const int *src, *in_ptr;
   int n_nodes;
   int last;
+  unsigned long long* timing;   // diagnostics (-DAGD_F16_TIMING): [57 + phase] cycles of CTA 0 / thread 0, summed over launches
 };
+
+#ifdef AGD_F16_TIMING
+#define GIN_TICK(i)                                                                   \
+  if (a.timing != nullptr && tid == 0 && blockIdx.x == 0) {                           \
+    const long long t_ = clock64();                                                   \
+    atomicAdd(a.timing + 57 + (i), static_cast<unsigned long long>(t_ - t_prev));     \
+    t_prev = t_;                                                                      \
+  }
+#else
+#define GIN_TICK(i)
+#endif
 
 constexpr int GIN_LD = 132;   // padded row stride of the gathered message tile
 constexpr size_t TC_GIN_SMEM = 1024 + 131072 + (TM * GIN_LD + 256) * sizeof(float) + 256;
@@ -354,6 +366,9 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_g2b + 128);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef AGD_F16_TIMING
+  long long t_prev = clock64();
+#endif
   const int quad = warp & 3, part = warp >> 2;
   const int my_row = quad * 32 + lane;
   const int n_rows = a.n_nodes;
@@ -380,6 +395,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
   cx.w_phase = 0; cx.m_phase = 0; cx.tid = tid;
   const float ope = __ldg(a.w.sc);
   constexpr uint32_t IMG = 2 * 128 * 128 * 4;
+  GIN_TICK(0);   // prologue
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t r = static_cast<int64_t>(tile) * TM + my_row;
@@ -432,7 +448,9 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
       }
       *reinterpret_cast<float4*>(s_tile + rr * GIN_LD + lane * 4) = acc;
     }
+    GIN_TICK(1);   // own gather
     __syncthreads();
+    GIN_TICK(2);   // waiting for the slowest warp
     // ---- each thread lifts its row quarter into TMEM
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -445,7 +463,9 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
       }
       st_split16(cx.trow, part * 32 + c * 16, t);
     }
+    GIN_TICK(3);   // lift into TMEM
     cx.layer(128, 128);
+    GIN_TICK(4);   // layer 1
     if (tid == 0) cx.stream(a.tG2, IMG);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -456,7 +476,9 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
       for (int j = 0; j < 16; ++j) t[j] = relu_(v[j] + s_g1b[n0 + j]);
       st_split16(cx.trow, n0, t);
     }
+    GIN_TICK(5);   // epilogue 1
     cx.layer(128, 128);
+    GIN_TICK(6);   // layer 2
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       float v[16];
@@ -483,6 +505,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    GIN_TICK(0);   // epilogue 2 + tile sync (booked with the prologue: the counter block has 7 slots)
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(cx.tmem, TMEM_COLS);
@@ -494,6 +517,7 @@ void launch_gin_layer_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w,
   a.tG1 = w.gin[layer].tG1; a.tG2 = w.gin[layer].tG2;
   a.x_in = x_in; a.x_out = x_out; a.ea = b.ea_loc; a.src = b.lc_src; a.in_ptr = b.lc_in_ptr;
   a.n_nodes = b.n_atoms;
+  a.timing = c.f16_timing;
   a.last = (layer == c.num_convs_local - 1) ? 1 : 0;
   int tiles = (b.n_atoms + TM - 1) / TM;
   const int grid = tiles < c.num_sms ? tiles : c.num_sms;

@@ -37,7 +37,19 @@ struct TcNode16Args {
   float* xcat;        // [N][192]
   int scaled;
   int* range_flag;
+  unsigned long long* timing;   // diagnostics (-DAGD_F16_TIMING): [40 + phase] cycles of CTA 0 / thread 0, summed over launches
 };
+
+#ifdef AGD_F16_TIMING
+#define NODE_TICK(i)                                                                  \
+  if (a.timing != nullptr && tid == 0 && blockIdx.x == 0) {                           \
+    const long long t_ = clock64();                                                   \
+    atomicAdd(a.timing + 40 + (i), static_cast<unsigned long long>(t_ - t_prev));     \
+    t_prev = t_;                                                                      \
+  }
+#else
+#define NODE_TICK(i)
+#endif
 
 constexpr size_t TC_NODE16_SMEM = 1024 + 2 * NIMG_128 + (128 * 3 + 64 * 2 + 128 + 64 + 1024 + 1024 + 512 + 4096) * sizeof(float) + 256;
 
@@ -105,6 +117,9 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef AGD_F16_TIMING
+  long long t_prev = clock64();
+#endif
   const int quad = warp & 3, part = warp >> 2;
   const int my_row = quad * 32 + lane;
   const int n_rows = a.n_nodes;
@@ -159,6 +174,7 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
     iL1a = __ldg(a.nnsc + 0); iL1b = __ldg(a.nnsc + 1);
   }
   __half2 amax = __floats2half2_rn(0.f, 0.f);
+  NODE_TICK(0);   // prologue
 
   // the first two layers of the first tile
   if (tid == 0 && static_cast<int>(blockIdx.x) < n_tiles) {
@@ -200,7 +216,9 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
         }
         node_store_split32(cx.trow, part * 16, t, lo_scale, amax);
       }
+      NODE_TICK(1);   // agg load + split
       cx.layer<128, 128>();                                    // L2a
+      NODE_TICK(2);
       if (tid == 0) cx.stream(a.hL2b, NIMG_HALF);
       {
         uint32_t v[32];
@@ -209,11 +227,13 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
         tmem_ld32(cx.trow + C16_D + n0, v);
         wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) t[j] = ssp(fmaf(__uint_as_float(v[j]), iL2a, s_l2ab[n0 + j]), beta_act);
+        for (int j = 0; j < 32; ++j) t[j] = ssp_fast(fmaf(__uint_as_float(v[j]), iL2a, s_l2ab[n0 + j]), beta_act);
         node_store_split32(cx.trow, part * 16, t, lo_scale, amax);
       }
       // ---- 2. first half of lin: xp = t1 . LIN[0:128]
+      NODE_TICK(3);   // epilogue L2a
       cx.layer<128, 128>();                                    // LINa
+      NODE_TICK(4);
       if (tid == 0) cx.stream(a.hLINb, NIMG_128);
       float xp[32];
       {
@@ -234,7 +254,9 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
         }
         node_store_split32(cx.trow, part * 16, t, lo_scale, amax);
       }
+      NODE_TICK(5);   // xp + agg2 load
       cx.layer<64, 128>();                                     // L2b (K = 64)
+      NODE_TICK(6);
       if (tid == 0) cx.stream(a.hA1, NIMG_HALF);
       {
         uint32_t v[32];
@@ -243,11 +265,13 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
         tmem_ld32(cx.trow + C16_D + n0, v);
         wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) t[j] = ssp(fmaf(__uint_as_float(v[j]), iL2b, s_l2bb[n0 + j]), beta_act);
+        for (int j = 0; j < 32; ++j) t[j] = ssp_fast(fmaf(__uint_as_float(v[j]), iL2b, s_l2bb[n0 + j]), beta_act);
         node_store_split32(cx.trow, part * 16, t, lo_scale, amax);
       }
       // ---- 4. second half of lin: xc = xp + t2 . LIN[128:256] + b
+      NODE_TICK(7);   // epilogue L2b
       cx.layer<128, 128>();                                    // LINb
+      NODE_TICK(8);
       if (tid == 0) {
         if (has_next) cx.stream(a.nhL1a, NIMG_128);
         else if (more) cx.stream(a.hL2a, NIMG_128);
@@ -263,10 +287,20 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
         node_store_split32(cx.trow, part * 16, xc, lo_scale, amax);
       }
       // ---- 5. attention gate
+      NODE_TICK(9);   // epilogue LINb
       cx.layer<128, 64>();                                     // A1
+      NODE_TICK(10);
       if (tid == 0) {
         if (has_next) cx.stream(a.nhL1b, NIMG_HALF);
         else if (more) cx.stream(a.hLINa, NIMG_128);
+      }
+      // the residual input h: requested here, two block-wide barriers ahead of its use (a load cannot be hoisted across them
+      // by the compiler, and with the L1 carved down to almost nothing it is an L2 round trip)
+      float4 hold[8];
+      {
+        const float4* ph = reinterpret_cast<const float4*>(a.h + (valid ? r : 0) * HID + part * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) hold[q] = valid ? ph[q] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       {
         uint32_t v[16];
@@ -279,7 +313,7 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
         s_part[part * 128 + my_row] = acc;
       }
       __syncthreads();
-      const float gate = sigmoidf_(((s_part[my_row] + s_part[128 + my_row]) + (s_part[256 + my_row] + s_part[384 + my_row])) + a2b);
+      const float gate = sigmoid_fast(((s_part[my_row] + s_part[128 + my_row]) + (s_part[256 + my_row] + s_part[384 + my_row])) + a2b);
       // ---- 6. adaptive scaling: r8 = relu(S1^T y), s = sigmoid(S2^T r8), out = y * s
       float r8[8];
 #pragma unroll
@@ -297,21 +331,20 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
       for (int j = 0; j < 8; ++j)
         r8[j] = relu_((s_r8[(0 * 8 + j) * 128 + my_row] + s_r8[(1 * 8 + j) * 128 + my_row]) +
                       (s_r8[(2 * 8 + j) * 128 + my_row] + s_r8[(3 * 8 + j) * 128 + my_row]));
-      const float4* ph = reinterpret_cast<const float4*>(a.h + (valid ? r : 0) * HID + part * 32);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 ho = valid ? ph[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float hv[4] = {ho.x, ho.y, ho.z, ho.w};
+        const float hv[4] = {hold[q].x, hold[q].y, hold[q].z, hold[q].w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int k = q * 4 + u;
           float s = 0.f;
 #pragma unroll
           for (int j = 0; j < 8; ++j) s = fmaf(r8[j], s_S2[j * 128 + part * 32 + k], s);
-          hnew[k] = hv[u] + xc[k] * sigmoidf_(s);
+          hnew[k] = hv[u] + xc[k] * sigmoid_fast(s);
         }
       }
     }
+    NODE_TICK(11);   // gate + adaptive scaling
     // ---- 7. write h
     if (valid) {
       float4* ph = reinterpret_cast<float4*>(a.h + r * HID + part * 32);
@@ -321,7 +354,9 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
     // ---- 8. next block's x = LeakyReLU(BN(lin1(h)))
     if (has_next) {
       node_store_split32(cx.trow, part * 16, hnew, lo_scale, amax);
+      NODE_TICK(12);   // h store + split
       cx.layer<128, 128>();                                    // next L1a
+      NODE_TICK(13);
       if (tid == 0 && more) cx.stream(a.first ? a.nhL1a : a.hL2a, NIMG_128);
       {
         uint32_t v[32];
@@ -338,7 +373,9 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
                                  leaky02(fmaf(__uint_as_float(v[q * 4 + 3]), iL1a, s_l1ab[n0 + q * 4 + 3])));
         }
       }
+      NODE_TICK(14);   // epilogue L1a
       cx.layer<128, 64>();   // next L1b; A still holds h
+      NODE_TICK(15);
       if (tid == 0 && more) cx.stream(a.first ? a.nhL1b : a.hLINa, a.first ? NIMG_HALF : NIMG_128);
       {
         uint32_t v[16];
@@ -359,6 +396,7 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    NODE_TICK(16);   // epilogue L1b
   }
   if (f16_out_of_range(amax)) atomicOr(a.range_flag, 1);
   __syncthreads();
@@ -387,6 +425,7 @@ void launch_schnet_node_f16(const LaunchCtx& c, const BatchDev& b, const ModelW&
   }
   a.scaled = f16_lo_shift() != 0;
   a.range_flag = b.counters + 4;
+  a.timing = c.f16_timing;
   int tiles = (b.n_atoms + TM - 1) / TM;
   const int grid = tiles < c.num_sms ? tiles : c.num_sms;
   tc_node16_kernel<<<grid, TCN16_THREADS, TC_NODE16_SMEM, c.stream>>>(a);

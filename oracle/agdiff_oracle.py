@@ -12,7 +12,7 @@ the oracle is pinned against outputs of the reference itself: ``oracle/make_gold
 the UNMODIFIED reference modules in the build container (third-party wheels replaced by the
 stand-ins in ``oracle/ref_shims.py``) and commits its outputs under ``tests/golden/``;
 ``tests/test_oracle_golden.py`` checks this restatement against them (bit-exact for edge
-lists, <= 2e-6 relative for fp32 tensors) and ``tests/test_oracle_vs_reference.py`` re-checks
+lists, <= 2e-6 relative for fp32 tensors) and ``tests/test_host.py::test_oracle_matches_reference_forward`` re-checks
 against the live reference whenever ``/root/reference`` is present.
 
 Third-party arithmetic restated here because it is absent from ``/root/reference`` and

@@ -6,7 +6,7 @@ Only runs in the build container; the committed fixtures travel to the GPU box.
 
 Weights are not stored (5.4 MB): they are regenerated from ``torch.manual_seed(seed)`` through
 ``get_model`` -- the product twin reproduces the reference's random init bit-for-bit
-(tests/test_oracle_vs_reference.py) and every fixture carries a float64 checksum of the
+(tests/test_host.py::test_oracle_matches_reference_forward) and every fixture carries a float64 checksum of the
 state_dict so a mismatch is detected on the GPU box.
 """
 from __future__ import annotations
