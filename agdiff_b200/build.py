@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
 LIB_PATH = os.path.join(HERE, "libagdiff_b200.so")
-SOURCES = ["api.cu", "edges.cu", "encoder.cu", "schnet.cu", "tc_filter.cu", "tc_filter16.cu", "tc_cfconv.cu", "tc_mlp16.cu", "tc_mlp.cu", "tc_node.cu", "tc_node16.cu", "gin.cu", "step.cu"]
+SOURCES = ["api.cu", "edges.cu", "encoder.cu", "schnet.cu", "tc_filter.cu", "tc_filter16.cu", "tc_cfconv.cu", "tc_mlp16.cu", "tc_mlp.cu", "tc_node.cu", "tc_node16.cu", "gin.cu", "step.cu", "ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -61,6 +62,7 @@ struct agd_handle {
   int f16_mlp = 1;
   int f16_pair = 1;
   int f16_node = 1;
+  int local_pairs = 1;
   int f16_debug_filt = 0;
   unsigned long long* f16_timing = nullptr;
   int mlp_act = 0;  // AGD_ACT_* of the pair MLPs (agd_set_option "mlp_act")
@@ -156,6 +158,7 @@ static LaunchCtx make_ctx(agd_handle* h) {
   c.f16_mlp = (c.use_tc == 2) ? h->f16_mlp : 0;
   c.f16_pair = (c.use_tc == 2) ? h->f16_pair : 0;
   c.f16_node = (c.use_tc == 2) ? h->f16_node : 0;
+  c.local_pairs = h->local_pairs;
   c.f16_debug_filt = h->f16_debug_filt;
   c.f16_timing = h->f16_timing;
   c.cutoff = h->cfg.cutoff;
@@ -187,13 +190,28 @@ struct Nvtx {
 };
 
 // ------------------------------------------------------------------ launch sequences
-static void run_local_branch(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos, const float** h_out) {
+// Local branch (dualenc.py:212-236).  Pair mode: the local edge list holds every bond / 2-hop / 3-hop pair in both directions, and
+// everything the edge encoder and the pair MLP see is symmetric in the direction - |pos_i - pos_j| (squares of negated
+// differences: the same bits), the edge type, h_i * h_j - so both run once per undirected pair over a "view" of the batch whose
+// local edge list is the list of representative edges, and their results are handed to both directions afterwards
+// (bit-identical to evaluating every directed edge).  The GIN gather in between reads edge_attr through the pair map.
+static void run_local_branch(const LaunchCtx& c, const BatchDev& b_in, const ModelW& w, const float* pos, const float** h_out) {
   Nvtx r_all("agd.local_branch");
+  const bool pairs = c.local_pairs && b_in.n_pairs > 0 && b_in.lc_len_in == nullptr;
+  const_cast<BatchDev&>(b_in).pairs_used = pairs ? 1 : 0;
+  BatchDev v = b_in;   // what the encoder and the pair MLP see
+  BatchDev b = b_in;   // what the GIN layers see
+  if (pairs) {
+    v.n_local = b_in.n_pairs;
+    v.lc_src = b_in.lp_src; v.lc_dst = b_in.lp_dst; v.lc_type = b_in.lp_type; v.lc_canon = b_in.lp_ident;
+    v.lc_len = b_in.lp_len; v.lcc_len = b_in.lp_scratch; v.sl_csc = b_in.lp_s; v.sl_canon = b_in.lp_scratch;
+    b.lc_ea_idx = b_in.lp_of;
+  }
   {
   Nvtx r("agd.edge_encoder.local");
-  if (c.f16_mlp) launch_encoder_local_f16(c, b, w, pos);
-  else if (c.use_tc) launch_encoder_local_tc(c, b, w, pos);
-  else launch_encoder_local(c, b, w, pos);
+  if (c.f16_mlp) launch_encoder_local_f16(c, v, w, pos);
+  else if (c.use_tc) launch_encoder_local_tc(c, v, w, pos);
+  else launch_encoder_local(c, v, w, pos);
   }
   const float* x_in = b.gx0;
   float* x_out = b.gx1;
@@ -208,9 +226,10 @@ static void run_local_branch(const LaunchCtx& c, const BatchDev& b, const ModelW
     }
   }
   Nvtx r_pair("agd.pair_mlp.local");
-  if (c.f16_pair) launch_pair_local_f16(c, b, w, x_in);
-  else if (c.use_tc && c.mlp_act == 0) launch_pair_local_tc(c, b, w, x_in);
-  else launch_pair_local(c, b, w, x_in);
+  if (c.f16_pair) launch_pair_local_f16(c, v, w, x_in);
+  else if (c.use_tc && c.mlp_act == 0) launch_pair_local_tc(c, v, w, x_in);
+  else launch_pair_local(c, v, w, x_in);
+  if (pairs) launch_local_pairs_expand(c, b_in);
   if (h_out) *h_out = x_in;
 }
 
@@ -287,6 +306,7 @@ int agd_create(const agd_config* cfg, agd_handle** out) {
   if (const char* e = std::getenv("AGD_F16_MLP")) h->f16_mlp = (e[0] != '0');
   if (const char* e = std::getenv("AGD_F16_PAIR")) h->f16_pair = (e[0] != '0');
   if (const char* e = std::getenv("AGD_F16_NODE")) h->f16_node = (e[0] != '0');
+  if (const char* e = std::getenv("AGD_LOCAL_PAIRS")) h->local_pairs = (e[0] != '0');
   if (const char* e = std::getenv("AGD_F16_DEBUG")) h->f16_debug_filt = std::atoi(e);
   if (const char* e = std::getenv("AGD_TC_FILTERS")) h->use_tc = (e[0] == '0') ? 0 : (e[0] == '1') ? 1 : 2;
   CUDA_TRY(cudaGetLastError());
@@ -354,8 +374,8 @@ struct Carver {
 
 static void carve(BatchDev& d, Carver& c) {
   const size_t N = (size_t)d.n_atoms, E = (size_t)(d.cap > 0 ? d.cap : 1), L = (size_t)(d.n_local > 0 ? d.n_local : 1);
-  d.adj = c.take<unsigned>(N * MAXW);
-  d.adjT = c.take<unsigned>(N * MAXW);
+  d.adj = c.take<unsigned>(N * (size_t)d.mw);
+  d.adjT = c.take<unsigned>(N * (size_t)d.mw);
   d.in_deg = c.take<int>(N);
   d.out_deg = c.take<int>(N);
   d.in_ptr = c.take<int>(N + 1);
@@ -387,6 +407,14 @@ static void carve(BatchDev& d, Carver& c) {
   d.agg = c.take<float>(N * 192);
   d.gx0 = c.take<float>(N * HID);
   d.gx1 = c.take<float>(N * HID);
+  d.lp_of = c.take<int>(L);
+  d.lp_src = c.take<int>(L);
+  d.lp_dst = c.take<int>(L);
+  d.lp_type = c.take<int>(L);
+  d.lp_ident = c.take<int>(L);
+  d.lp_len = c.take<float>(L);
+  d.lp_s = c.take<float>(L);
+  d.lp_scratch = c.take<float>(L);
   d.hmax = c.take<float>(N);
 }
 
@@ -401,6 +429,65 @@ static int check_desc(const agd_batch_desc* d) {
 
 extern "C" {
 
+// 32-bit words per adjacency row for a batch: 8 while every molecule has <= 256 atoms, 16 up to AGD_MAX_MOL_ATOMS; -1 beyond
+// (mol_ptr is a device array; this runs once per batch / per bond-order call, never on the step path).
+static int adjacency_words(const int32_t* mol_ptr_dev, int n_mols, int* largest_out = nullptr) {
+  std::vector<int32_t> hp((size_t)n_mols + 1);
+  if (cudaMemcpy(hp.data(), mol_ptr_dev, sizeof(int32_t) * hp.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  int largest = 0;
+  for (int m = 0; m < n_mols; ++m) largest = std::max(largest, hp[m + 1] - hp[m]);
+  if (largest_out) *largest_out = largest;
+  if (largest > AGD_MAX_MOL_ATOMS) return -1;
+  return largest <= 256 ? 8 : 16;
+}
+
+// Pair map of the local edges (CSC order: grouped by destination, sources ascending): edge (j -> i) with j > i shares the pair of
+// its twin (i -> j) when that exists with the same type; every other edge is the representative of its own pair.
+static int build_local_pairs(BatchDev& v) {
+  v.n_pairs = 0;
+  const size_t L = (size_t)v.n_local, N = (size_t)v.n_atoms;
+  if (L == 0) return AGD_OK;
+  std::vector<int> src(L), dst(L), typ(L), ptr(N + 1);
+  CUDA_TRY(cudaMemcpy(src.data(), v.lc_src, L * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(dst.data(), v.lc_dst, L * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(typ.data(), v.lc_type, L * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(ptr.data(), v.lc_in_ptr, (N + 1) * 4, cudaMemcpyDeviceToHost));
+  std::vector<int> of(L, -1), ps, pd, pt;
+  ps.reserve(L / 2 + 1); pd.reserve(L / 2 + 1); pt.reserve(L / 2 + 1);
+  auto twin = [&](size_t e) -> long {   // the edge dst[e] -> src[e], found in the segment of destination src[e]
+    const int j = src[e], i = dst[e];
+    if (j < 0 || (size_t)j >= N) return -1;
+    const int* lo = src.data() + ptr[j];
+    const int* hi = src.data() + ptr[j + 1];
+    const int* it = std::lower_bound(lo, hi, i);
+    if (it == hi || *it != i) return -1;
+    const long t = it - src.data();
+    return (dst[t] == j && typ[t] == typ[e]) ? t : -1;
+  };
+  auto open_pair = [&](size_t e) {
+    of[e] = (int)ps.size();
+    ps.push_back(src[e]); pd.push_back(dst[e]); pt.push_back(typ[e]);
+  };
+  for (size_t e = 0; e < L; ++e)
+    if (src[e] < dst[e]) open_pair(e);
+  for (size_t e = 0; e < L; ++e) {
+    if (of[e] >= 0) continue;
+    const long t = (src[e] > dst[e]) ? twin(e) : -1;
+    if (t >= 0 && of[t] >= 0 && src[t] < dst[t]) of[e] = of[t];
+    else open_pair(e);
+  }
+  const size_t P = ps.size();
+  std::vector<int> ident(P);
+  for (size_t p = 0; p < P; ++p) ident[p] = (int)p;
+  CUDA_TRY(cudaMemcpy(v.lp_of, of.data(), L * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(v.lp_src, ps.data(), P * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(v.lp_dst, pd.data(), P * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(v.lp_type, pt.data(), P * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(v.lp_ident, ident.data(), P * 4, cudaMemcpyHostToDevice));
+  v.n_pairs = (int)P;
+  return AGD_OK;
+}
+
 int64_t agd_batch_workspace_bytes(const agd_handle* h, const agd_batch_desc* d) {
   (void)h;
   if (check_desc(d) != AGD_OK) return -1;
@@ -409,6 +496,7 @@ int64_t agd_batch_workspace_bytes(const agd_handle* h, const agd_batch_desc* d) 
   t.n_mols = d->n_mols;
   t.cap = d->edge_capacity;
   t.n_local = d->n_local;
+  t.mw = 16;   // upper bound (the row width is only known once the molecule sizes have been read)
   Carver c{nullptr};
   carve(t, c);
   return (int64_t)c.off;
@@ -428,6 +516,15 @@ int agd_batch_create(agd_handle* h, const agd_batch_desc* d, agd_batch** out) {
   v.st_src = d->st_src; v.st_dst = d->st_dst; v.st_type = d->st_type; v.st_in_ptr = d->st_in_ptr;
   v.lc_src = d->lc_src; v.lc_dst = d->lc_dst; v.lc_type = d->lc_type; v.lc_in_ptr = d->lc_in_ptr;
   v.lc_canon = d->lc_canon; v.lc_out_ptr = d->lc_out_ptr; v.lc_cdst = d->lc_cdst;
+  {
+    int largest = 0;
+    v.mw = adjacency_words(d->mol_ptr, d->n_mols, &largest);
+    if (v.mw < 0) {
+      delete b;
+      if (v.mw == -2) return fail(AGD_ERR_CUDA, "cannot read mol_ptr (device pointer expected)");
+      return fail(AGD_ERR_CAPACITY, "a molecule of " + std::to_string(largest) + " atoms exceeds AGD_MAX_MOL_ATOMS (" + std::to_string(AGD_MAX_MOL_ATOMS) + ")");
+    }
+  }
   Carver sz{nullptr};
   carve(v, sz);
   b->slab_bytes = (int64_t)sz.off;
@@ -444,6 +541,7 @@ int agd_batch_create(agd_handle* h, const agd_batch_desc* d, agd_batch** out) {
     delete b;
     return fail(AGD_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
   }
+  if (build_local_pairs(v) != AGD_OK) v.n_pairs = 0;   // (pair mode is an optimisation: without the map the local branch evaluates every directed edge)
   *out = b;
   return AGD_OK;
 }
@@ -466,7 +564,7 @@ static int check_ready(agd_handle* h, agd_batch* b) {
 static int check_overflow(agd_batch* b) {
   int flag[4];
   CUDA_TRY(cudaMemcpy(flag, b->d.counters, sizeof(flag), cudaMemcpyDeviceToHost));
-  if (flag[3] != 0) return fail(AGD_ERR_CAPACITY, "a molecule exceeds AGD_MAX_MOL_ATOMS (256)");
+  if (flag[3] != 0) return fail(AGD_ERR_CAPACITY, "a molecule exceeds the adjacency row width chosen for the batch (mol_ptr changed after agd_batch_create?)");
   if ((int64_t)flag[0] > b->d.cap) return fail(AGD_ERR_CAPACITY, "edge count exceeded the declared capacity");
   return AGD_OK;
 }
@@ -627,6 +725,11 @@ int agd_sample(agd_handle* h, agd_batch* b, float* pos, const agd_sample_params*
     // chunk graph are launched alternately.
     int chunk = 8;
     if (const char* e = std::getenv("AGD_GRAPH_CHUNK")) chunk = std::atoi(e) > 0 ? std::atoi(e) : 1;
+    // Which step types replay graphs (A/B switches).  Local-only steps (7 short kernels, 0.7 ms) are launch-bound: graphs win
+    // (0.70 vs 0.75 ms per step).  For global steps (45 kernels, 5 ms) it is a wash: 66.6 vs 65.3 conformers/s on the bench batch.
+    bool graph_for[2] = {true, true};
+    if (const char* e = std::getenv("AGD_GRAPH_GLOBAL")) graph_for[1] = (e[0] != '0');
+    if (const char* e = std::getenv("AGD_GRAPH_LOCAL")) graph_for[0] = (e[0] != '0');
     int64_t per_step_launches[2] = {0, 0};
     // longest run of equal-type steps decides whether a chunk graph is worth building
     int longest[2] = {0, 0};
@@ -638,7 +741,7 @@ int agd_sample(agd_handle* h, agd_batch* b, float* pos, const agd_sample_params*
       s = e;
     }
     for (int g = 0; g < 2; ++g) {
-      if (!(g ? any_global : any_local)) continue;
+      if (!(g ? any_global : any_local) || !graph_for[g]) continue;
       for (int kind = 0; kind < 2; ++kind) {   // 0: one step, 1: chunk
         if (kind == 1 && (chunk < 2 || longest[g] < chunk)) continue;
         cudaGraph_t graph = nullptr;
@@ -660,6 +763,12 @@ int agd_sample(agd_handle* h, agd_batch* b, float* pos, const agd_sample_params*
     int flip = 0;
     for (int s = 0; s < p->n_steps && e == cudaSuccess && !nan_seen;) {
       const int g = p->use_global[s] ? 1 : 0;
+      if (!graph_for[g]) {
+        one_step(g == 1);
+        s += 1;
+        e = poll();
+        continue;
+      }
       int run = 1;
       while (run < chunk && s + run < p->n_steps && (p->use_global[s + run] != 0) == (g == 1)) ++run;
       if (run == chunk && guard.exec_chunk[g][0]) {
@@ -715,8 +824,11 @@ int agd_extend_bond_order(const int32_t* mol_ptr, int32_t n_mols, int32_t n_atom
                           int32_t* out_count, const int32_t* out_ptr, int32_t* out_dst, int32_t* out_type, void* stream) {
   if (!mol_ptr || !bond_ptr || n_mols <= 0) return fail(AGD_ERR_INVALID, "bad arguments");
   if (!out_ptr && !out_count) return fail(AGD_ERR_INVALID, "count pass needs out_count");
+  const int mw = adjacency_words(mol_ptr, n_mols);
+  if (mw == -2) return fail(AGD_ERR_CUDA, "cannot read mol_ptr (device pointer expected)");
+  if (mw < 0) return fail(AGD_ERR_CAPACITY, "a molecule exceeds AGD_MAX_MOL_ATOMS");
   int rc = launch_extend_bond_order((cudaStream_t)stream, mol_ptr, n_mols, n_atoms, bond_ptr, bond_dst, bond_type, order,
-                                    num_bond_types, out_count, out_ptr, out_dst, out_type);
+                                    num_bond_types, out_count, out_ptr, out_dst, out_type, mw);
   if (rc) return fail(rc, "edge order must be 1..3");
   CUDA_TRY(cudaGetLastError());
   return AGD_OK;
@@ -735,6 +847,7 @@ int agd_op_cfconv_aggregate(const float* x, const float* W, const int32_t* src, 
   c.f16_mlp = 0;
   c.f16_pair = 0;
   c.f16_node = 0;
+  c.local_pairs = 0;
   c.f16_debug_filt = 0;
   c.f16_timing = nullptr;
   c.mlp_act = 0;
@@ -746,6 +859,24 @@ int agd_op_cfconv_aggregate(const float* x, const float* W, const int32_t* src, 
 int agd_op_eq_transform(const float* score, const float* pos, const int32_t* src, const int32_t* dst, const float* length,
                         int64_t n_edges, int32_t n_nodes, float* out, void* stream) {
   launch_eq_transform((cudaStream_t)stream, score, pos, src, dst, length, n_edges, n_nodes, out);
+  CUDA_TRY(cudaGetLastError());
+  return AGD_OK;
+}
+
+int agd_op_gin_message(const float* x, const float* ea, const int32_t* src, const int32_t* in_ptr, int32_t n_nodes, float eps,
+                       float* out, void* stream) {
+  if (!x || !ea || !src || !in_ptr || !out || n_nodes < 0) return fail(AGD_ERR_INVALID, "bad arguments");
+  launch_gin_message((cudaStream_t)stream, x, ea, nullptr, src, in_ptr, n_nodes, eps, nullptr, out);
+  CUDA_TRY(cudaGetLastError());
+  return AGD_OK;
+}
+
+int agd_op_eq_transform_segments(const float* pos, const float* score_out, const int32_t* col_of_out, const int32_t* out_ptr,
+                                 const float* score_in, const int32_t* row_of_in, const int32_t* in_ptr, int32_t n_nodes,
+                                 float* out, void* stream) {
+  if (!pos || !score_out || !col_of_out || !out_ptr || !score_in || !row_of_in || !in_ptr || !out || n_nodes < 0)
+    return fail(AGD_ERR_INVALID, "bad arguments");
+  launch_eq_transform_segments((cudaStream_t)stream, pos, score_out, col_of_out, out_ptr, score_in, row_of_in, in_ptr, n_nodes, out);
   CUDA_TRY(cudaGetLastError());
   return AGD_OK;
 }
@@ -765,7 +896,16 @@ int64_t agd_debug_fetch(agd_batch* b, const char* name, float* dst, int64_t capa
   else if (s == "h_global") { src = d.h; n = (int64_t)d.n_atoms * HID; }
   else if (s == "xcat") { src = d.xcat; n = (int64_t)d.n_atoms * 192; }
   else if (s == "agg") { src = d.agg; n = (int64_t)d.n_atoms * 192; }
-  else if (s == "ea_local") { src = d.ea_loc; n = (int64_t)d.n_local * HID; }
+  else if (s == "ea_local") {
+    n = (int64_t)d.n_local * HID;
+    if (d.pairs_used) {   // ea_loc holds one row per pair: hand out the rows in local-edge order
+      if (n > capacity) return fail(AGD_ERR_CAPACITY, "destination too small");
+      launch_gather_rows128(b->h->stream, d.ea_loc, d.lp_of, d.n_local, dst);
+      if (cudaStreamSynchronize(b->h->stream) != cudaSuccess) return fail(AGD_ERR_CUDA, "gather failed");
+      return n;
+    }
+    src = d.ea_loc;
+  }
   else if (s == "h_local") { src = (b->h->cfg.num_convs_local % 2) ? d.gx1 : d.gx0; n = (int64_t)d.n_atoms * HID; }
   else if (s == "e_len") { src = d.e_len; n = n_edges; }
   else if (s == "s_csc") { src = d.s_csc; n = n_edges; }
@@ -790,6 +930,7 @@ int agd_set_option(agd_handle* h, const char* name, int value) {
   else if (std::strcmp(name, "f16_mlp") == 0) h->f16_mlp = value ? 1 : 0;
   else if (std::strcmp(name, "f16_pair") == 0) h->f16_pair = value ? 1 : 0;
   else if (std::strcmp(name, "f16_node") == 0) h->f16_node = value ? 1 : 0;
+  else if (std::strcmp(name, "local_pairs") == 0) h->local_pairs = value ? 1 : 0;
   else if (std::strcmp(name, "mlp_act") == 0) {
     if (value < 0 || value >= AGD_ACT_COUNT) return fail(AGD_ERR_INVALID, "unknown mlp_act id");
     h->mlp_act = value;

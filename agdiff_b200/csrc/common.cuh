@@ -20,7 +20,6 @@ constexpr int TM = 128;         // rows per tile
 constexpr int LDA = TM + 4;     // padded leading dimension of the transposed activation tile
 constexpr int NT = 256;         // threads per CTA of the tile kernels
 constexpr int KC = 16;          // weight rows per cp.async chunk
-constexpr int MAXW = 8;         // 32-bit words per adjacency row (AGD_MAX_MOL_ATOMS / 32)
 constexpr int AS_FLOATS = HID * LDA;          // one activation tile (K up to 128)
 constexpr int WS_FLOATS = 2 * KC * 128;       // weight ring
 constexpr float LN2F = 0.69314718055994530942f;

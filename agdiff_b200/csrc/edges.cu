@@ -5,7 +5,8 @@
 // the only floating-point decision is d2 < r*r, evaluated as (dx*dx + dy*dy) + dz*dz with
 // explicitly un-fused fp32 operations.
 //
-// One CTA owns one molecule (<= 256 atoms): its adjacency is a bit matrix in shared memory
+// One CTA owns one molecule: its adjacency is a bit matrix in shared memory with MW 32-bit words per row - MW = 8 (<= 256 atoms:
+// every GEOM molecule) or, when the batch holds a larger molecule, MW = 16 (<= AGD_MAX_MOL_ATOMS = 512), chosen per batch -
 // (row i = sources of destination i) built by warp ballots, the transpose gives out-degrees and
 // canonical ranks by popcount, and a batch-wide exclusive scan turns per-atom degrees into CSC /
 // canonical segment pointers without any host-visible size.
@@ -14,17 +15,19 @@
 
 namespace agd {
 
-constexpr int MAXA = AGD_MAX_MOL_ATOMS;
 
+template <int MAXW>
 __global__ void __launch_bounds__(128) adjacency_kernel(const float* __restrict__ pos, const int* __restrict__ mol_ptr,
                                                         const int* __restrict__ st_src, const int* __restrict__ st_dst,
                                                         const int* __restrict__ st_in_ptr, float r2,
                                                         unsigned* __restrict__ adj, unsigned* __restrict__ adjT,
                                                         int* __restrict__ in_deg, int* __restrict__ out_deg,
                                                         int* __restrict__ counters) {
-  __shared__ float sp[MAXA * 3];
-  __shared__ unsigned A[MAXA * MAXW];
-  __shared__ unsigned AT[MAXA * MAXW];
+  constexpr int MAXA = MAXW * 32;
+  extern __shared__ unsigned edge_smem[];
+  unsigned* A = edge_smem;                 // [MAXA][MAXW]
+  unsigned* AT = A + MAXA * MAXW;          // [MAXA][MAXW]
+  float* sp = reinterpret_cast<float*>(AT + MAXA * MAXW);   // [MAXA][3]
   const int m = blockIdx.x;
   const int a0 = mol_ptr[m], a1 = mol_ptr[m + 1];
   const int n = a1 - a0;
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(1024) degree_scan_kernel(const int* __restrict
 
 // one warp per destination atom: emit its in-edges (sources ascending) into the CSC arrays and
 // mirror every record to its canonical slot.
+template <int MAXW>
 __global__ void __launch_bounds__(256) edge_fill_kernel(const float* __restrict__ pos, const int* __restrict__ mol_ptr,
                                                         const int* __restrict__ atom_mol, int n_atoms,
                                                         const int* __restrict__ st_src, const int* __restrict__ st_type,
@@ -233,17 +237,36 @@ __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict
     dst[i] = src[i];
 }
 
+template <int MAXW>
+constexpr size_t adjacency_smem() { return (size_t)(MAXW * 32) * (2 * MAXW * sizeof(unsigned) + 3 * sizeof(float)); }
+
 void launch_build_edges(const LaunchCtx& c, const BatchDev& b, const float* pos) {
   const float r2 = c.cutoff * c.cutoff;
-  adjacency_kernel<<<b.n_mols, 128, 0, c.stream>>>(pos, b.mol_ptr, b.st_src, b.st_dst, b.st_in_ptr, r2, b.adj, b.adjT,
-                                                   b.in_deg, b.out_deg, b.counters);
+  if (b.mw <= 8)
+    adjacency_kernel<8><<<b.n_mols, 128, adjacency_smem<8>(), c.stream>>>(pos, b.mol_ptr, b.st_src, b.st_dst, b.st_in_ptr, r2, b.adj, b.adjT,
+                                                                          b.in_deg, b.out_deg, b.counters);
+  else {
+    static bool attr = false;   // (idempotent; a race only repeats the call)
+    if (!attr) {
+      cudaFuncSetAttribute(adjacency_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adjacency_smem<16>());
+      attr = true;
+    }
+    adjacency_kernel<16><<<b.n_mols, 128, adjacency_smem<16>(), c.stream>>>(pos, b.mol_ptr, b.st_src, b.st_dst, b.st_in_ptr, r2, b.adj, b.adjT,
+                                                                            b.in_deg, b.out_deg, b.counters);
+  }
   note_launch(c, "edges.adjacency");
   degree_scan_kernel<<<1, 1024, 0, c.stream>>>(b.in_deg, b.out_deg, b.n_atoms, b.in_ptr, b.out_ptr, b.counters);
   note_launch(c, "edges.scan");
   const int warps_per_cta = 8;
-  edge_fill_kernel<<<(b.n_atoms + warps_per_cta - 1) / warps_per_cta, 256, 0, c.stream>>>(
-      pos, b.mol_ptr, b.atom_mol, b.n_atoms, b.st_src, b.st_type, b.st_in_ptr, b.adj, b.adjT, b.in_ptr, b.out_ptr,
-      b.e_src, b.e_dst, b.e_type, b.e_canon, b.e_len, b.c_src, b.c_dst, b.c_type, b.c_len);
+  const int fill_grid = (b.n_atoms + warps_per_cta - 1) / warps_per_cta;
+  if (b.mw <= 8)
+    edge_fill_kernel<8><<<fill_grid, 256, 0, c.stream>>>(pos, b.mol_ptr, b.atom_mol, b.n_atoms, b.st_src, b.st_type, b.st_in_ptr, b.adj, b.adjT,
+                                                         b.in_ptr, b.out_ptr, b.e_src, b.e_dst, b.e_type, b.e_canon, b.e_len, b.c_src, b.c_dst,
+                                                         b.c_type, b.c_len);
+  else
+    edge_fill_kernel<16><<<fill_grid, 256, 0, c.stream>>>(pos, b.mol_ptr, b.atom_mol, b.n_atoms, b.st_src, b.st_type, b.st_in_ptr, b.adj, b.adjT,
+                                                          b.in_ptr, b.out_ptr, b.e_src, b.e_dst, b.e_type, b.e_canon, b.e_len, b.c_src, b.c_dst,
+                                                          b.c_type, b.c_len);
   note_launch(c, "edges.fill");
 }
 
@@ -266,15 +289,18 @@ void launch_export_edges(const LaunchCtx& c, const BatchDev& b, const agd_forwar
 // _extend_graph_order (common.py:135-205): pairs at shortest directed path length k in [2, order]
 // get type num_bond_types + k - 1; direct bonds keep the (summed) bond type; zero types vanish.
 // One CTA per molecule, reachability sets as bit rows.  out_ptr == nullptr: count pass.
+template <int MAXW>
 __global__ void __launch_bounds__(128) bond_order_kernel(const int* __restrict__ mol_ptr, const int* __restrict__ bond_ptr,
                                                          const int* __restrict__ bond_dst,
                                                          const int* __restrict__ bond_type, int order, int num_types,
                                                          int* __restrict__ out_count, const int* __restrict__ out_ptr,
                                                          int* __restrict__ out_dst, int* __restrict__ out_type) {
-  __shared__ unsigned R1[MAXA * MAXW];    // adj | I
-  __shared__ unsigned CUR[MAXA * MAXW];   // reach within k hops
-  __shared__ unsigned NXT[MAXA * MAXW];
-  __shared__ unsigned char HOP[MAXA * MAXA / 4];  // 2 bits per pair would do; 0..3 packed 4 per byte
+  constexpr int MAXA = MAXW * 32;
+  extern __shared__ unsigned edge_smem[];
+  unsigned* R1 = edge_smem;                // [MAXA][MAXW] adj | I
+  unsigned* CUR = R1 + MAXA * MAXW;        // reach within k hops
+  unsigned* NXT = CUR + MAXA * MAXW;
+  unsigned char* HOP = reinterpret_cast<unsigned char*>(NXT + MAXA * MAXW);   // [MAXA * MAXA / 4] hop count 0..3 per pair, 4 pairs per byte
   const int m = blockIdx.x;
   const int a0 = mol_ptr[m], n = mol_ptr[m + 1] - a0;
   const int tid = threadIdx.x;
@@ -363,11 +389,23 @@ __global__ void __launch_bounds__(128) bond_order_kernel(const int* __restrict__
 
 int launch_extend_bond_order(cudaStream_t s, const int* mol_ptr, int n_mols, int n_atoms, const int* bond_ptr,
                              const int* bond_dst, const int* bond_type, int order, int num_bond_types, int* out_count,
-                             const int* out_ptr, int* out_dst, int* out_type) {
+                             const int* out_ptr, int* out_dst, int* out_type, int mw) {
   if (order > 3 || order < 1) return AGD_ERR_INVALID;
   (void)n_atoms;
-  bond_order_kernel<<<n_mols, 128, 0, s>>>(mol_ptr, bond_ptr, bond_dst, bond_type, order, num_bond_types, out_count,
-                                           out_ptr, out_dst, out_type);
+  if (mw <= 8) {
+    constexpr size_t smem = 256 * (3 * 8 * sizeof(unsigned)) + 256 * 256 / 4;
+    bond_order_kernel<8><<<n_mols, 128, smem, s>>>(mol_ptr, bond_ptr, bond_dst, bond_type, order, num_bond_types, out_count, out_ptr,
+                                                   out_dst, out_type);
+  } else {
+    constexpr size_t smem = 512 * (3 * 16 * sizeof(unsigned)) + 512 * 512 / 4;
+    static bool attr = false;   // (idempotent; a race only repeats the call)
+    if (!attr) {
+      cudaFuncSetAttribute(bond_order_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr = true;
+    }
+    bond_order_kernel<16><<<n_mols, 128, smem, s>>>(mol_ptr, bond_ptr, bond_dst, bond_type, order, num_bond_types, out_count, out_ptr,
+                                                    out_dst, out_type);
+  }
   return AGD_OK;
 }
 

@@ -25,6 +25,7 @@ struct GinArgs {
   float* x_out;
   const float* ea;     // [n_local][128] edge_attr of the local edges, CSC order
   const int *src, *in_ptr;
+  const int* ea_idx;   // row of `ea` for each CSC local edge (pair mode), or nullptr: the edge's own row
   int n_nodes;
   int last;
 };
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(NT, 2) gin_layer_kernel(const GinArgs a) {
       const int e0 = a.in_ptr[node], e1 = a.in_ptr[node + 1];
       for (int e = e0; e < e1; ++e) {
         const float* xs = a.x_in + (size_t)__ldg(a.src + e) * HID;
-        const float* ee = a.ea + (size_t)e * HID;
+        const float* ee = a.ea + (size_t)(a.ea_idx ? __ldg(a.ea_idx + e) : e) * HID;
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] += relu_(__ldg(xs + lane + 32 * j) + __ldg(ee + lane + 32 * j));
       }
@@ -87,6 +88,7 @@ void launch_gin_layer(const LaunchCtx& c, const BatchDev& b, const ModelW& w, in
   a.ea = b.ea_loc;
   a.src = b.lc_src;
   a.in_ptr = b.lc_in_ptr;
+  a.ea_idx = b.lc_ea_idx;
   a.n_nodes = b.n_atoms;
   a.last = (layer == c.num_convs_local - 1) ? 1 : 0;
   gin_layer_kernel<<<(b.n_atoms + TM - 1) / TM, NT, GIN_SMEM, c.stream>>>(a);

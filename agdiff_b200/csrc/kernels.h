@@ -74,7 +74,8 @@ struct BatchDev {
   const int *st_src, *st_dst, *st_type, *st_in_ptr;
   const int *lc_src, *lc_dst, *lc_type, *lc_in_ptr, *lc_canon, *lc_out_ptr, *lc_cdst;
   // edge builder scratch
-  unsigned *adj, *adjT;          // [N][MAXW]
+  unsigned *adj, *adjT;          // [N][mw]
+  int mw;                        // 32-bit words per adjacency row: 8 (every molecule <= 256 atoms) or 16 (<= AGD_MAX_MOL_ATOMS)
   int *in_deg, *out_deg;         // [N]
   int *in_ptr, *out_ptr;         // [N+1]
   int* counters;                 // [0]=n_edges [1]=step index [2]=first NaN step
@@ -97,6 +98,14 @@ struct BatchDev {
   float* cw_all;                 // [2 * num_convs][cap] envelope * distance weight per CFConv layer (AGD_MODE_F16)
   float* filt;                   // [cap][192]  CFConv filters of the current block (conv1 | conv2)
   float *h, *xcat, *agg;         // [N][128], [N][192], [N][192]
+  // pair mode of the local branch: local edges come in both directions with identical inputs (length, type, h_src * h_dst), so the
+  // edge encoder and the pair MLP run once per undirected pair (representative orientation src < dst; an edge without a twin is its own pair)
+  int n_pairs;                   // 0: unavailable
+  int pairs_used;                // the last evaluation ran in pair mode (ea_loc holds pair rows)
+  int *lp_of;                    // [n_local] pair of each CSC local edge
+  int *lp_src, *lp_dst, *lp_type, *lp_ident;   // [n_pairs] representative edges; lp_ident[p] = p
+  float *lp_len, *lp_s, *lp_scratch;           // [n_pairs] length / score per pair; write-only twin for the kernels' second output order
+  const int* lc_ea_idx;          // GIN: row of ea_loc for each CSC local edge (pair mode) or nullptr
   float *gx0, *gx1;              // [N][128] GIN ping-pong
   float* hmax;                   // [N] per-atom max |h| feeding the pair kernels' per-row scale (AGD_MODE_F16)
   // per-step schedule (device copy)
@@ -129,6 +138,7 @@ struct LaunchCtx {
   unsigned long long* f16_timing;   // diagnostics: per-phase cycle counters of the f16 filter kernels (device, 64 values) or nullptr
   int f16_mlp;     // use_tc == 2: edge encoder on the fp16 two-slot kernels (tc_mlp16.cu)
   int f16_pair;    // use_tc == 2: pair MLPs on the fp16 two-slot kernels
+  int local_pairs; // local branch: encoder + pair MLP once per undirected pair (default 1)
   int f16_node;    // use_tc == 2: SchNet node chain on the fp16 kernel with double-buffered weight streaming (tc_node16.cu)
   int f16_fuse;    // use_tc == 2: both CFConv layers of a block + the aggregation in one launch (tc_cfconv.cu; no filt tensor, no aggregate kernel)
   int mlp_act;     // activation of the pair MLPs (AGD_ACT_*); anything but relu runs them on the fp32 FFMA kernel
@@ -142,7 +152,7 @@ void launch_build_edges(const LaunchCtx& c, const BatchDev& b, const float* pos)
 void launch_export_edges(const LaunchCtx& c, const BatchDev& b, const agd_forward_out& out, bool with_scores);
 int launch_extend_bond_order(cudaStream_t s, const int* mol_ptr, int n_mols, int n_atoms, const int* bond_ptr,
                              const int* bond_dst, const int* bond_type, int order, int num_bond_types, int* out_count,
-                             const int* out_ptr, int* out_dst, int* out_type);
+                             const int* out_ptr, int* out_dst, int* out_type, int mw);
 // encoder.cu
 void launch_encoder_global(const LaunchCtx& c, const BatchDev& b, const ModelW& w);
 void launch_encoder_local(const LaunchCtx& c, const BatchDev& b, const ModelW& w, const float* pos);
@@ -178,6 +188,12 @@ void launch_gin_layer(const LaunchCtx& c, const BatchDev& b, const ModelW& w, in
 // step.cu
 void launch_step(const LaunchCtx& c, const BatchDev& b, float* pos, const StepParams& p);
 void launch_advance(const LaunchCtx& c, const BatchDev& b);
+void launch_gin_message(cudaStream_t s, const float* x, const float* ea, const int* ea_idx, const int* src, const int* in_ptr, int n_nodes,
+                        float eps, const float* one_plus_eps_dev, float* out);
+void launch_local_pairs_expand(const LaunchCtx& c, const BatchDev& b);
+void launch_gather_rows128(cudaStream_t s, const float* src, const int* idx, int n, float* dst);
+void launch_eq_transform_segments(cudaStream_t s, const float* pos, const float* s_out, const int* col_of_out, const int* out_ptr,
+                                  const float* s_in, const int* row_of_in, const int* in_ptr, int n_nodes, float* out);
 void launch_eq_transform(cudaStream_t s, const float* score, const float* pos, const int* src, const int* dst,
                          const float* len, int64_t n_edges, int n_nodes, float* out);
 

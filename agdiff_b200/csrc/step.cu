@@ -12,7 +12,7 @@ namespace agd {
 
 constexpr int STEP_THREADS = 256;                 // four threads per atom
 constexpr int STEP_ATOMS = STEP_THREADS / 4;      // atoms per sweep of the CTA
-constexpr int STEP_MAX_PER_THREAD = AGD_MAX_MOL_ATOMS / STEP_ATOMS;
+// (atoms per quad of threads: 4 for molecules of <= 256 atoms, 8 up to AGD_MAX_MOL_ATOMS = 512 - template parameter of the kernel)
 
 __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -75,6 +75,7 @@ __device__ __forceinline__ void clip3(float& x, float& y, float& z, float limit)
 // local out, global in, global out; each in CSC / canonical order), the quad combines them in a fixed order with shuffles -
 // eq = (in + out) per branch - so the result is bit-reproducible and does not depend on batch composition, while the four
 // dependent-load chains of an atom run side by side (the one-thread-per-atom version was latency-bound at 6 % issue rate).
+template <int STEP_MAX_PER_THREAD>
 __global__ void __launch_bounds__(STEP_THREADS) langevin_step_kernel(const StepArgs a) {
   __shared__ float red[3][STEP_THREADS / 32];
   __shared__ int s_bad;
@@ -213,7 +214,8 @@ void launch_step(const LaunchCtx& c, const BatchDev& b, float* pos, const StepPa
   a.counters = b.counters;
   a.nan_mol = b.nan_mol;
   a.p = p;
-  langevin_step_kernel<<<b.n_mols, STEP_THREADS, 0, c.stream>>>(a);
+  if (b.mw <= 8) langevin_step_kernel<256 / STEP_ATOMS><<<b.n_mols, STEP_THREADS, 0, c.stream>>>(a);
+  else langevin_step_kernel<AGD_MAX_MOL_ATOMS / STEP_ATOMS><<<b.n_mols, STEP_THREADS, 0, c.stream>>>(a);
   note_launch(c, "step.langevin");
 }
 

@@ -338,6 +338,7 @@ struct TcGinArgs {
   float* x_out;
   const float* ea;
   const int *src, *in_ptr;
+  const int* ea_idx;  // row of `ea` for each CSC local edge (pair mode: both directions of a bond share one row), or nullptr
   int n_nodes;
   int last;
   unsigned long long* timing;   // diagnostics (-DAGD_F16_TIMING): [57 + phase] cycles of CTA 0 / thread 0, summed over launches
@@ -357,6 +358,15 @@ struct TcGinArgs {
 constexpr int GIN_LD = 132;   // padded row stride of the gathered message tile
 constexpr size_t TC_GIN_SMEM = 1024 + 131072 + (TM * GIN_LD + 256) * sizeof(float) + 256;
 
+// one lane's float4 of the edge_attr row of local edge e: streamed (evict-first) when every edge has its own row, through the
+// pair map with default caching when a row serves both directions of a bond (the second reader may still find it in L2)
+template <bool PAIRS>
+__device__ __forceinline__ float4 ldg_ea(const float* ea, const int* ea_idx, int e, int lane) {
+  if (!PAIRS) return __ldcs(reinterpret_cast<const float4*>(ea + (size_t)e * HID) + lane);
+  return __ldg(reinterpret_cast<const float4*>(ea + (size_t)__ldg(ea_idx + e) * HID) + lane);
+}
+
+template <bool PAIRS>
 __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer (LDS, not generic LD)
@@ -415,7 +425,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             xv[u] = __ldg(reinterpret_cast<const float4*>(a.x_in + (size_t)__ldg(a.src + e + u) * HID) + lane);
-            ev[u] = __ldcs(reinterpret_cast<const float4*>(a.ea + (size_t)(e + u) * HID) + lane);
+            ev[u] = ldg_ea<PAIRS>(a.ea, a.ea_idx, e + u, lane);
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
@@ -432,7 +442,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
             ev[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (u < n) {
               xv[u] = __ldg(reinterpret_cast<const float4*>(a.x_in + (size_t)__ldg(a.src + e + u) * HID) + lane);
-              ev[u] = __ldcs(reinterpret_cast<const float4*>(a.ea + (size_t)(e + u) * HID) + lane);
+              ev[u] = ldg_ea<PAIRS>(a.ea, a.ea_idx, e + u, lane);
             }
           }
 #pragma unroll
@@ -464,6 +474,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
       st_split16(cx.trow, part * 32 + c * 16, t);
     }
     GIN_TICK(3);   // lift into TMEM
+  
     cx.layer(128, 128);
     GIN_TICK(4);   // layer 1
     if (tid == 0) cx.stream(a.tG2, IMG);
@@ -515,13 +526,14 @@ void launch_gin_layer_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& w,
   TcGinArgs a{};
   a.w = w.gin[layer];
   a.tG1 = w.gin[layer].tG1; a.tG2 = w.gin[layer].tG2;
-  a.x_in = x_in; a.x_out = x_out; a.ea = b.ea_loc; a.src = b.lc_src; a.in_ptr = b.lc_in_ptr;
+  a.x_in = x_in; a.x_out = x_out; a.ea = b.ea_loc; a.src = b.lc_src; a.in_ptr = b.lc_in_ptr; a.ea_idx = b.lc_ea_idx;
   a.n_nodes = b.n_atoms;
   a.timing = c.f16_timing;
   a.last = (layer == c.num_convs_local - 1) ? 1 : 0;
   int tiles = (b.n_atoms + TM - 1) / TM;
   const int grid = tiles < c.num_sms ? tiles : c.num_sms;
-  tc_gin_kernel<<<grid, TCN_THREADS, TC_GIN_SMEM, c.stream>>>(a);
+  if (a.ea_idx) tc_gin_kernel<true><<<grid, TCN_THREADS, TC_GIN_SMEM, c.stream>>>(a);
+  else tc_gin_kernel<false><<<grid, TCN_THREADS, TC_GIN_SMEM, c.stream>>>(a);
   note_launch(c, "gin.layer_tc");
 }
 
@@ -549,7 +561,8 @@ void launch_schnet_node_tc(const LaunchCtx& c, const BatchDev& b, const ModelW& 
 
 void set_tc_node_attributes() {
   cudaFuncSetAttribute(tc_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_NODE_SMEM);
-  cudaFuncSetAttribute(tc_gin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GIN_SMEM);
+  cudaFuncSetAttribute(tc_gin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GIN_SMEM);
+  cudaFuncSetAttribute(tc_gin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_GIN_SMEM);
 }
 
 }  // namespace agd

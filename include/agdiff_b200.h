@@ -21,7 +21,8 @@ extern "C" {
 
 #define AGD_ABI_VERSION 1
 #define AGD_HIDDEN 128            /* hidden_dim; pinned by Linear(256, hidden) at schnet.py:190-192 */
-#define AGD_MAX_MOL_ATOMS 256     /* per-molecule limit of the adjacency bit-matrix edge builder    */
+#define AGD_MAX_MOL_ATOMS 512     /* per-molecule limit of the adjacency bit-matrix edge builder (rows of 8 x 32 bits while every
+                                   * molecule of the batch has <= 256 atoms, 16 x 32 otherwise)      */
 #define AGD_MAX_RADIUS_NBRS 32    /* torch_cluster default used by common.py:217                    */
 
 enum {
@@ -179,6 +180,17 @@ int agd_op_cfconv_aggregate(const float* x /*dev [N][F]*/, const float* W /*dev 
                             const int32_t* in_ptr, int32_t n_nodes, int32_t F, float* out /*dev [N][F]*/, void* stream);
 int agd_op_eq_transform(const float* score /*dev [E]*/, const float* pos, const int32_t* src, const int32_t* dst,
                         const float* length, int64_t n_edges, int32_t n_nodes, float* out /*dev [N][3]*/, void* stream);
+
+/* GIN aggregation, gin.py:76-96 (GINEConv.forward + message): out_i = (1 + eps) * x_i + sum_{e in in(i)} relu(x[src_e] + ea_e)
+ * over CSC-sorted edges, 128 features - the gather phase of the fused GIN layer kernel as a kernel of its own. */
+int agd_op_gin_message(const float* x /*dev [N][128]*/, const float* ea /*dev [E][128]*/, const int32_t* src /*dev [E]*/,
+                       const int32_t* in_ptr /*dev [N+1]*/, int32_t n_nodes, float eps, float* out /*dev [N][128]*/, void* stream);
+/* eq_transform, geometry.py:9-17, in the atomics-free form the step kernel uses: the edge list is given twice, sorted by row
+ * (out-segments: out_ptr, the col of each edge, its score) and sorted by col (in-segments: in_ptr, the row of each edge, its
+ * score); lengths are recomputed from pos. */
+int agd_op_eq_transform_segments(const float* pos /*dev [N][3]*/, const float* score_out, const int32_t* col_of_out,
+                                 const int32_t* out_ptr, const float* score_in, const int32_t* row_of_in, const int32_t* in_ptr,
+                                 int32_t n_nodes, float* out /*dev [N][3]*/, void* stream);
 
 /* debugging / tests: copy an internal per-batch tensor to a caller device buffer.  Names:
  * "g2", "h_global", "h_local", "ea_local", "xcat", "agg", "filt".  Returns element count or <0. */

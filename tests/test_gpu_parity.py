@@ -506,6 +506,117 @@ def test_op_eq_transform():
     assert_close(out, ref, rtol=1e-4, atol_scale=1e-5, what="eq_transform")
 
 
+def _random_csr(N, E, gen):
+    """random directed multigraph without self loops, as (row, col) with the CSC (sorted by col) and CSR (sorted by row) views"""
+    ei = torch.randint(0, N, (2, E), generator=gen)
+    ei = ei[:, ei[0] != ei[1]]
+    return ei
+
+
+def test_op_gin_message():
+    """stand-alone GIN aggregation == (1 + eps) x_i + sum relu(x_j + e_ji)  (gin.py:76-96), incl. nodes without in-edges"""
+    import ctypes as C
+    from agdiff_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(5)
+    N, E = 700, 9000
+    ei = _random_csr(N - 50, E, gen)          # the last 50 nodes have no edges
+    order = torch.argsort(ei[1], stable=True)  # CSC: grouped by destination
+    src, dst = ei[0][order], ei[1][order]
+    in_ptr = torch.zeros(N + 1, dtype=torch.int64)
+    in_ptr[1:] = torch.cumsum(torch.bincount(dst, minlength=N), 0)
+    x = torch.randn(N, 128, generator=gen)
+    ea = torch.randn(src.numel(), 128, generator=gen)
+    eps = 0.25
+    ref = (1 + eps) * x.double()
+    ref.index_add_(0, dst, torch.relu(x.double()[src] + ea.double()))
+    out = torch.empty(N, 128, device=DEV)
+    a = [t.to(DEV).contiguous() for t in (x, ea, src.to(torch.int32), in_ptr.to(torch.int32))]
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.agd_op_gin_message(*[C.c_void_p(t.data_ptr()) for t in a], N, C.c_float(eps), C.c_void_p(out.data_ptr()), st))
+    torch.cuda.synchronize()
+    assert_close(out, ref, rtol=1e-5, atol_scale=1e-6, what="gin message")
+
+
+def test_op_eq_transform_segments():
+    """atomics-free eq_transform over sorted segments == the reference's two scatter_adds (geometry.py:9-17), and bitwise
+    reproducible from run to run"""
+    import ctypes as C
+    from agdiff_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(6)
+    N, E = 500, 9000
+    pos = torch.randn(N, 3, generator=gen) * 3
+    ei = _random_csr(N, E, gen)
+    s = torch.randn(ei.size(1), generator=gen)
+    ln = O.edge_lengths(pos, ei).unsqueeze(-1)
+    ref = O.eq_transform(s.double().unsqueeze(-1), pos.double(), ei, ln.double())
+    o_out = torch.argsort(ei[0], stable=True)
+    o_in = torch.argsort(ei[1], stable=True)
+    ptr = lambda idx: torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(torch.bincount(idx, minlength=N), 0)]).to(torch.int32)
+    a = [pos, s[o_out], ei[1][o_out].to(torch.int32), ptr(ei[0]), s[o_in], ei[0][o_in].to(torch.int32), ptr(ei[1])]
+    a = [t.to(DEV).contiguous() for t in a]
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    outs = []
+    for _ in range(2):
+        out = torch.empty(N, 3, device=DEV)
+        _lib.check(lib.agd_op_eq_transform_segments(*[C.c_void_p(t.data_ptr()) for t in a], N, C.c_void_p(out.data_ptr()), st))
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    assert_close(outs[0], ref, rtol=1e-4, atol_scale=1e-5, what="eq_transform (segments)")
+
+
+# ------------------------------------------------------------------------------- molecules beyond 256 atoms
+def _large_batch(sizes, seed=31):
+    rng = np.random.default_rng(seed)
+    mols = []
+    for n in sizes:
+        n_heavy = max(2, int(np.rint(n * 0.55)))
+        mols.append(synth._random_molecule(rng, n, n_heavy, (6, 6, 6, 7, 8, 16), max(0, n_heavy // 8)))
+    return mols
+
+
+def test_large_molecules_up_to_512_atoms():
+    """molecules of 300 and 450 atoms next to small ones (the batch switches to 16-word adjacency rows): bond-order extension on
+    device == host, edge lists bit-exact (the 33-neighbour truncation scans 450 candidates), forward and a short trajectory
+    across the global-start boundary against the oracle"""
+    m, sd = _cuda_model("drugs", 2021, 0)
+    raw = _large_batch([300, 12, 450, 40])
+    mols = [graph.extend_bond_order_host(x) for x in raw]
+    # device bond-order extension on the raw bond graphs
+    zr, bir, btr, br, Gr = graph.collate(raw, 1)
+    row, col, typ = m._static_edges(zr.numel(), bir.to(DEV), btr.to(DEV), br.to(DEV), True)
+    z, bi, bt, b, G = graph.collate(mols, 1)
+    assert torch.equal(torch.stack([row, col]).cpu(), bi) and torch.equal(typ.cpu(), bt)
+    pos = O.center_pos(torch.randn(z.numel(), 3, generator=torch.Generator().manual_seed(3)) * 4.0, b)
+    with torch.no_grad():
+        ref = O.forward(sd, CONFIGS["drugs"], z, pos, bi, bt, b, extend_order=False)
+    out = m(z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), None, return_edges=True, extend_order=False)
+    assert torch.equal(out[2].cpu(), ref[2]) and torch.equal(out[3].cpu(), ref[3])
+    ng, nl = fp32_noise(sd, CONFIGS["drugs"], z, pos, bi, bt, b, ref)
+    assert_close(out[1], ref[1], what="edge_inv_local", extra_atol=4 * nl)
+    assert_close(out[0], ref[0], what="edge_inv_global", extra_atol=4 * ng)
+    n_steps, t_start = 12, 2017                  # sigma crosses 0.5 at i = 2012
+    noise = torch.randn(n_steps, z.numel(), 3, generator=torch.Generator().manual_seed(4))
+    kw = dict(extend_order=False, n_steps=n_steps, step_lr=1e-6, clip=1000.0, clip_local=20.0, global_start_sigma=0.5,
+              w_global=1.0, noise=noise, t_start=t_start, scale_init=False)
+    with torch.no_grad():
+        rpos, _ = O.sample(sd, CONFIGS["drugs"], z, pos, bi, bt, b, G, keep_traj=False, **kw)
+    gpos, _ = m.langevin_dynamics_sample_diffusion(z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), G, **kw)
+    r = kabsch_free_rmsd(gpos, rpos, b)
+    assert float(r.max()) <= 1e-3, "RMSD %.3e A" % float(r.max())
+
+
+def test_molecule_beyond_the_limit_is_refused():
+    m, sd = _cuda_model("qm9", 2021, 0)
+    mols = _large_batch([513])
+    z, bi, bt, b, G = graph.collate(mols, 1)
+    pos = torch.randn(z.numel(), 3)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        m(z.to(DEV), pos.to(DEV), bi.to(DEV), bt.to(DEV), b.to(DEV), None, extend_order=False)
+
+
 # ------------------------------------------------------------------------------- degenerate inputs
 def test_degenerate_batches():
     """single-atom molecules, molecules without bonds, and geometries with no edge at all (empty tensors, like the reference)"""

@@ -2,7 +2,9 @@
 
 Synthetic CSR graphs, in-degree 32, N = E/32, uniform features in [-1, 1], seed 0:
   (i)  CFConv message + aggregate, F in {128, 64, 192}: agg_i = sum_e x[src_e] * W_e        (agd_op_cfconv_aggregate)
-  (iii) eq_transform: out[row] += dd*s, out[col] -= dd*s                                    (agd_op_eq_transform)
+  (ii) GIN message + aggregate: out_i = (1+eps) x_i + sum_e relu(x[src_e] + ea_e), 128 features  (agd_op_gin_message)
+  (iii) eq_transform: out[row] += dd*s, out[col] -= dd*s, with atomics                       (agd_op_eq_transform)
+        and in the atomics-free sorted-segment form the step kernel uses                     (agd_op_eq_transform_segments)
 Prints achieved GB/s with the algorithmic bytes of SURVEY 8d (indices as int32) against MEASURED_PEAKS.json.
 Each timing: 3 warm-up + 10 timed launches with CUDA events; inputs are larger than L2 from E >= 3e5 (F=128).
 """
@@ -64,6 +66,23 @@ for E in (100_000, 300_000, 1_000_000, 3_000_000, 10_000_000):
     t = timeit(lambda: _lib.check(lib.agd_op_eq_transform(P(sc), P(pos), P(src), P(dst), P(ln), E, N, P(out), st)))
     byts = E * (4 + 8 + 4 + 24) + N * 24
     rows.append(("eq_transform (atomics)", E, t * 1e6, byts / t / 1e9))
+    # (iii b) the same edge list as sorted segments: CSC as built (sorted by col = dst) and re-sorted by row for the out-segments
+    order = torch.argsort(src.long(), stable=True)
+    col_of_out = dst[order].contiguous()
+    out_ptr = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(torch.bincount(src.long(), minlength=N), 0)]).to(torch.int32)
+    sc_out = sc[order].contiguous()
+    t = timeit(lambda: _lib.check(lib.agd_op_eq_transform_segments(P(pos), P(sc_out), P(col_of_out), P(out_ptr), P(sc), P(src), P(in_ptr), N, P(out), st)))
+    byts = 2 * E * (4 + 4 + 12) + N * (12 + 8 + 12)   # every edge is visited from both ends: score + index + the far position
+    rows.append(("eq_transform (segments)", E, t * 1e6, byts / t / 1e9))
+    del order, col_of_out, out_ptr, sc_out
+    # (ii) GIN message
+    x = (torch.rand(N, 128, generator=gen) * 2 - 1).to(dev)
+    ea = (torch.rand(E, 128, generator=gen) * 2 - 1).to(dev)
+    o = torch.empty(N, 128, device=dev)
+    t = timeit(lambda: _lib.check(lib.agd_op_gin_message(P(x), P(ea), P(src), P(in_ptr), N, C.c_float(0.1), P(o), st)))
+    byts = E * (512 + 512 + 4) + N * (512 + 512 + 4)
+    rows.append(("gin_message", E, t * 1e6, byts / t / 1e9))
+    del x, ea, o
 
 print("| kernel | edges | us/launch | algorithmic GB/s | frac of measured HBM peak (%.0f GB/s) |" % peak)
 print("|---|---|---|---|---|")
