@@ -881,6 +881,16 @@ int agd_op_eq_transform_segments(const float* pos, const float* score_out, const
   return AGD_OK;
 }
 
+int agd_op_kabsch_rmsd(const float* ref, const float* gen, const int32_t* sel, int32_t n_sel, int32_t n_atoms, int32_t n_ref,
+                       int32_t n_gen, float* out, void* stream) {
+  if (!ref || !gen || !out || n_atoms <= 0 || n_ref < 0 || n_gen < 0) return fail(AGD_ERR_INVALID, "bad arguments");
+  if (!sel) n_sel = n_atoms;
+  if (n_sel <= 0 || n_sel > n_atoms) return fail(AGD_ERR_INVALID, "atom selection must hold 1..n_atoms indices");
+  launch_kabsch_rmsd((cudaStream_t)stream, ref, gen, sel, n_sel, n_atoms, n_ref, n_gen, out);
+  CUDA_TRY(cudaGetLastError());
+  return AGD_OK;
+}
+
 int64_t agd_debug_fetch(agd_batch* b, const char* name, float* dst, int64_t capacity) {
   if (!b || !name || !dst) return fail(AGD_ERR_INVALID, "null argument");
   const BatchDev& d = b->d;

@@ -191,6 +191,8 @@ void launch_advance(const LaunchCtx& c, const BatchDev& b);
 void launch_gin_message(cudaStream_t s, const float* x, const float* ea, const int* ea_idx, const int* src, const int* in_ptr, int n_nodes,
                         float eps, const float* one_plus_eps_dev, float* out);
 void launch_local_pairs_expand(const LaunchCtx& c, const BatchDev& b);
+void launch_kabsch_rmsd(cudaStream_t s, const float* ref, const float* gen, const int* sel, int n_sel, int n_atoms, int n_ref, int n_gen,
+                        float* out);
 void launch_gather_rows128(cudaStream_t s, const float* src, const int* idx, int n, float* dst);
 void launch_eq_transform_segments(cudaStream_t s, const float* pos, const float* s_out, const int* col_of_out, const int* out_ptr,
                                   const float* s_in, const int* row_of_in, const int* in_ptr, int n_nodes, float* out);

@@ -137,4 +137,100 @@ void launch_gather_rows128(cudaStream_t s, const float* src, const int* idx, int
   gather_rows128_kernel<<<(int)blocks, 256, 0, s>>>(src, idx, n, dst);
 }
 
+// ---------------------------------------------------------------------------------------------------------------- COV / MAT
+// RMSD after optimal superposition (proper rotations only, like RDKit's alignment behind get_best_rmsd, utils/chem.py) for every
+// (reference conformer, generated conformer) pair of one molecule: covmat.py:16-34.  One warp per pair; lanes stride over the
+// selected atoms accumulating centroids, the 3 x 3 cross-covariance and the two inner products in fp64; lane 0 then gets the
+// largest eigenvalue of Horn's 4 x 4 quaternion key matrix (Jacobi rotations, fp64): rmsd^2 = (Ga + Gb - 2 lambda_max) / n.  No symmetry permutations (RDKit tries the molecule's automorphisms): an upper bound of
+// GetBestRMS, equal to it for molecules without non-trivial heavy-atom automorphisms.
+__global__ void __launch_bounds__(256) kabsch_rmsd_kernel(const float* __restrict__ ref, const float* __restrict__ gen,
+                                                          const int* __restrict__ sel, int n_sel, int n_atoms, int n_ref, int n_gen,
+                                                          float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pair < n_ref * n_gen; pair += warps) {
+    const int ir = pair / n_gen, ig = pair - ir * n_gen;
+    const float* A = ref + (size_t)ir * n_atoms * 3;
+    const float* B = gen + (size_t)ig * n_atoms * 3;
+    double v[17];   // sum a (3), sum b (3), sum a_i b_j (9), sum |a|^2, sum |b|^2
+#pragma unroll
+    for (int k = 0; k < 17; ++k) v[k] = 0.0;
+    for (int t = lane; t < n_sel; t += 32) {
+      const int at = sel ? sel[t] : t;
+      const double a[3] = {A[3 * at], A[3 * at + 1], A[3 * at + 2]};
+      const double b[3] = {B[3 * at], B[3 * at + 1], B[3 * at + 2]};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        v[i] += a[i];
+        v[3 + i] += b[i];
+        v[15] += a[i] * a[i];
+        v[16] += b[i] * b[i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v[6 + 3 * i + j] += a[i] * b[j];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 17; ++k)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) {
+      const double n = (double)n_sel;
+      double S[3][3];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) S[i][j] = v[6 + 3 * i + j] - v[i] * v[3 + j] / n;   // centred cross-covariance
+      const double Ga = v[15] - (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) / n;
+      const double Gb = v[16] - (v[3] * v[3] + v[4] * v[4] + v[5] * v[5]) / n;
+      const double Sxx = S[0][0], Sxy = S[0][1], Sxz = S[0][2], Syx = S[1][0], Syy = S[1][1], Syz = S[1][2], Szx = S[2][0],
+                   Szy = S[2][1], Szz = S[2][2];
+      // Horn's key matrix; its largest eigenvalue by cyclic Jacobi rotations.  (Newton on the characteristic polynomial - the
+      // usual QCP shortcut - loses half the digits when the top eigenvalue is degenerate, which is the case for every planar
+      // molecule and every 3-atom selection, and the square root below turns 1e-8 into 1e-4 A.)
+      double K[4][4] = {{Sxx + Syy + Szz, Syz - Szy, Szx - Sxz, Sxy - Syx},
+                        {Syz - Szy, Sxx - Syy - Szz, Sxy + Syx, Szx + Sxz},
+                        {Szx - Sxz, Sxy + Syx, -Sxx + Syy - Szz, Syz + Szy},
+                        {Sxy - Syx, Szx + Sxz, Syz + Szy, -Sxx - Syy + Szz}};
+      for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int p = 0; p < 4; ++p) {
+          diag += K[p][p] * K[p][p];
+          for (int q = p + 1; q < 4; ++q) off += K[p][q] * K[p][q];
+        }
+        if (off <= 1e-32 * diag || off == 0.0) break;
+        for (int p = 0; p < 3; ++p)
+          for (int q = p + 1; q < 4; ++q) {
+            const double apq = K[p][q];
+            if (apq == 0.0) continue;
+            const double theta = (K[q][q] - K[p][p]) / (2.0 * apq);
+            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+            for (int k = 0; k < 4; ++k) {   // K <- J^T K J, columns then rows
+              const double kp = K[k][p], kq = K[k][q];
+              K[k][p] = c * kp - sn * kq;
+              K[k][q] = sn * kp + c * kq;
+            }
+            for (int k = 0; k < 4; ++k) {
+              const double pk = K[p][k], qk = K[q][k];
+              K[p][k] = c * pk - sn * qk;
+              K[q][k] = sn * pk + c * qk;
+            }
+          }
+      }
+      double l = K[0][0];
+      for (int p = 1; p < 4; ++p) l = (K[p][p] > l || !(l == l)) ? K[p][p] : l;
+      double r2 = (Ga + Gb - 2.0 * l) / n;
+      if (!(r2 > 0.0)) r2 = (r2 != r2) ? r2 : 0.0;   // rounding below zero for identical conformers; NaN inputs stay NaN
+      out[pair] = (float)sqrt(r2);
+    }
+  }
+}
+
+void launch_kabsch_rmsd(cudaStream_t s, const float* ref, const float* gen, const int* sel, int n_sel, int n_atoms, int n_ref, int n_gen,
+                        float* out) {
+  const int64_t pairs = (int64_t)n_ref * n_gen;
+  if (pairs <= 0) return;
+  int64_t blocks = (pairs + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  kabsch_rmsd_kernel<<<(int)blocks, 256, 0, s>>>(ref, gen, sel, n_sel, n_atoms, n_ref, n_gen, out);
+}
+
 }  // namespace agd

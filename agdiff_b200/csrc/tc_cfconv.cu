@@ -13,24 +13,27 @@
 //   warps  0- 7  E  epilogue 1 of conv1, then of conv2: accumulator -> bias + ShiftedSoftplus (SFU) -> fp16 hi/lo' split -> written
 //                   back IN PLACE over the accumulator columns (a 16-column fp32 chunk becomes 8 hi + 8 lo' words = one k-block),
 //                   which is then the A operand of layer 2.  Nothing else: this is the MUFU-bound stage (2 per element).
-//   warps  8-11  D  drain of the layer-2 accumulators (x bias, x edge weight) into a ring of two 32-column shared-memory slabs
-//                   (thread = tile row).
-//   warps 12-18  R  CFConv aggregation from the ring: one warp per destination run, a quarter-warp per position-in-run mod 4,
-//                   lanes = float4 columns - the summation order of cfconv_aggregate_kernel (four round-robin partial sums per
-//                   destination, combined as (s0 + s1) + (s2 + s3)), which does not depend on where tile or CTA boundaries
-//                   fall, so the result equals the unfused path bit for bit.  The x rows of a run are gathered into registers
-//                   two 32-column passes ahead (double-buffered by pass parity): the L2 latency hides behind two slab periods.
-//                   All tiles of a CTA pass through these warps in order; the partial sums of a run cut by a tile boundary
-//                   wait in shared memory.
-//   warp  19     M  weights (176 KB, cp.async.bulk, once) and every tcgen05.mma: one elected lane issues a whole layer, with
-//                   compile-time TMEM addresses and descriptors that are constant offsets of one uniform base.
-//   warps 20-23  L  operand loader: thread = tile row, g2h row (32 x LDG.128, L1 bypass) -> tcgen05.st into the layer-1 operand
+//   warps  8-11  D  drain of the layer-2 accumulators (x 1/scale + bias, x edge weight) into a ring of two 32-column
+//                   shared-memory slabs (thread = tile row): six passes per tile, four for conv1 and two for conv2.
+//   warps 12-15  L  operand loader: thread = tile row, g2h row (32 x LDG.128, L1 bypass) -> tcgen05.st into the layer-1 operand
 //                   columns; the tile after next is pulled into L2 with cp.async.bulk.prefetch; bookkeeping of the tile for the
 //                   reducers (x-row offsets, destinations, run starts) - the loader runs a tile ahead of them.
+//   warps 16-25  R  CFConv aggregation from the ring, two teams of five warps: team 0 takes the even passes (slab 0), team 1 the
+//                   odd ones (slab 1).  One warp per destination run, a quarter-warp per position-in-run mod 4, lanes = float4
+//                   columns - the summation order of cfconv_aggregate_kernel (four round-robin partial sums per destination,
+//                   combined as (s0 + s1) + (s2 + s3)), which does not depend on where tile or CTA boundaries fall, so the
+//                   result equals the unfused path bit for bit.  The x rows of a run (10 per quarter-warp = 40 rows, 95 % of the
+//                   runs of a drug-like radius graph; longer runs continue on demand) are gathered into registers right after
+//                   the team's previous pass: the L2 latency hides behind the other team's slab period.  All tiles of a CTA
+//                   pass through these warps in order; the partial sums of a run cut by a tile boundary wait in shared
+//                   memory (double-buffered by tile parity).
+//   warp  26     M  weights (176 KB, cp.async.bulk, once) and every tcgen05.mma: one elected lane issues a whole layer, with
+//                   compile-time TMEM addresses and descriptors that are constant offsets of one uniform base.
 // A lone warp retires a dependent instruction only every ~4-6 cycles, so what bounds a role is the length of its per-tile
 // instruction stream; the split above keeps every stream under ~1000 instructions per 128-edge tile.
-// Registers: launched at 80 per thread; loader (48), epilogue (56) and drain (56) warpgroups give registers back, the two
-// reducer warpgroups take them (128): 2 passes x 44 rows x 16 B in flight per reducer warp.
+// Registers: launched at 72 per thread (896 threads); setmaxnreg moves them per warpgroup: E 56, D 48, L 56, R + M 96.  With
+// 224 KB of shared memory the L1 is ~0, so a single spilled value is an L2 round trip: every role is spill-free, and values
+// that would live across all role branches (shared-memory pointers) are recomputed per role (cf_sbase).
 //
 // TMEM (512 columns, one tile in flight, sub-tile pipelined):
 //   [  0,128) A1   layer-1 operand hi | lo' (K = 128)          free again once layer 1 of both nets has completed
@@ -38,7 +41,10 @@
 //   [256,320) Y1   conv2: the same, 64 columns
 //   [320,448) X2   conv1: layer-2 accumulator                   [448,512) Y2  conv2: layer-2 accumulator
 // Tensor-pipe order per tile: L1x, L1y, (wait E) L2x, (wait E) L2y - while E works on X1 the pipe runs L1y, while it works on
-// Y1 the pipe runs L2x; A drains tile j while the pipe and E are already on tile j+1.
+// Y1 the pipe runs L2x; D and R drain tile j while the pipe and E are already on tile j+1.
+// What was measured and NOT adopted (profiles/r02_cfconv_experiments.md): issuing layer 2 one tile late with layer 1 of conv1
+// split into two 64-column halves (E and D slow each other down: 2.70 vs 2.56 ms), the loader warps draining the odd passes
+// (their load latency lands in the drain path: 3.19 ms), per-tile address arrays in the reducers (spills or serialised LDS).
 #include "kernels.h"
 #include "tc_filter16.cuh"
 

@@ -192,6 +192,13 @@ int agd_op_eq_transform_segments(const float* pos /*dev [N][3]*/, const float* s
                                  const int32_t* out_ptr, const float* score_in, const int32_t* row_of_in, const int32_t* in_ptr,
                                  int32_t n_nodes, float* out /*dev [N][3]*/, void* stream);
 
+/* COV/MAT building block, utils/evaluation/covmat.py:16-34: out[i][j] = RMSD of generated conformer j onto reference conformer i
+ * after optimal superposition (proper rotation) over the selected atoms (sel = NULL: all; the reference compares heavy atoms).
+ * Atom order is taken as given - RDKit's GetBestRMS additionally minimises over the molecule's symmetry permutations. */
+int agd_op_kabsch_rmsd(const float* ref /*dev [n_ref][n_atoms][3]*/, const float* gen /*dev [n_gen][n_atoms][3]*/,
+                       const int32_t* sel /*dev [n_sel] or NULL*/, int32_t n_sel, int32_t n_atoms, int32_t n_ref, int32_t n_gen,
+                       float* out /*dev [n_ref][n_gen]*/, void* stream);
+
 /* debugging / tests: copy an internal per-batch tensor to a caller device buffer.  Names:
  * "g2", "h_global", "h_local", "ea_local", "xcat", "agg", "filt".  Returns element count or <0. */
 int64_t agd_debug_fetch(agd_batch* b, const char* name, float* dst_dev, int64_t capacity);

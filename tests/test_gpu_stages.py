@@ -335,3 +335,75 @@ def test_pair_mlp_activations_other_than_relu(act):
     ng, nl = fp32_noise(sd, cfg, z, pos, bi, bt, b, ref)
     assert_close(out[0], ref[0], what="edge_inv_global (%s)" % act, extra_atol=4 * ng)
     assert_close(out[1], ref[1], what="edge_inv_local (%s)" % act, extra_atol=4 * nl)
+
+
+# ------------------------------------------------------------------------------- COV / MAT
+def test_kabsch_rmsd_matrix_matches_numpy_oracle():
+    """aligned RMSD of every (reference, generated) pair vs the SVD oracle: rotated + translated copies (0), noisy copies,
+    a mirror image (must NOT align to 0: proper rotations only), heavy-atom selection, a planar and a 3-atom molecule"""
+    from agdiff_b200 import evaluation
+    from oracle import kabsch_oracle as K
+    rng = np.random.default_rng(0)
+
+    def rot():
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        return q * np.sign(np.linalg.det(q))
+
+    for n, planar in ((3, False), (17, False), (60, False), (181, False), (24, True)):
+        base = rng.normal(size=(n, 3)) * 2.0
+        if planar:
+            base[:, 2] = 0.0
+        ref = np.stack([base, base @ rot().T + rng.normal(size=3), base + 0.3 * rng.normal(size=(n, 3))])
+        gen = np.stack([base @ rot().T + 5.0, base * np.array([1.0, 1.0, -1.0]), base + 0.05 * rng.normal(size=(n, 3)),
+                        rng.normal(size=(n, 3)) * 2.0, base @ rot().T])
+        sel = np.sort(rng.choice(n, size=max(3, n // 2), replace=False)) if n > 3 else None
+        for s_ in (None, sel):
+            want = K.rmsd_confusion_matrix(ref, gen, s_)
+            got = evaluation.rmsd_matrix(ref, gen, s_).double().cpu().numpy()
+            assert got.shape == want.shape
+            assert np.abs(got - want).max() <= 2e-5 * max(1.0, want.max()), (n, planar, np.abs(got - want).max())
+        if not planar:
+            assert got[0, 0] < 1e-4 and want[0, 1] > 1e-2      # rotated copy aligns; the mirror image does not
+
+
+def test_covmat_evaluator_matches_oracle():
+    """CovMatEvaluator (covmat.py:76-171): filtering (disconnected smiles, too few generated conformers, missing keys), the
+    ratio cut, and COV-R / MAT-R / COV-P / MAT-P against the numpy restatement; evaluate_conf on one molecule"""
+    from agdiff_b200 import evaluation
+    from oracle import kabsch_oracle as K
+    rng = np.random.default_rng(1)
+    mols = synth.drugs_like(4, seed=12, force_max=False)
+    packed = []
+    for k, mol in enumerate(mols):
+        n = mol.num_nodes
+        n_ref = 2 + k
+        ref = rng.normal(size=(n_ref, n, 3)) * 1.5
+        gen = np.concatenate([ref + 0.1 * (j + 1) * rng.normal(size=ref.shape) for j in range(3)])   # 3 * n_ref >= ratio * n_ref
+        packed.append({"smiles": "C" * (k + 1), "atom_type": torch.as_tensor(mol.atom_type), "pos_ref": torch.tensor(ref).reshape(-1, 3).float(),
+                       "pos_gen": torch.tensor(gen).reshape(-1, 3).float()})
+    packed.append(dict(packed[0], smiles="CC.O"))                                              # disconnected: dropped
+    packed.append(dict(packed[1], pos_gen=packed[1]["pos_gen"][: mols[1].num_nodes]))          # 1 generated < ratio * n_ref: dropped
+    packed.append({"smiles": "C", "atom_type": packed[0]["atom_type"], "pos_ref": packed[0]["pos_ref"]})   # no pos_gen: dropped
+    log = []
+    ev = evaluation.CovMatEvaluator(thresholds=np.arange(0.05, 1.55, 0.05), ratio=2, print_fn=log.append)
+    res = ev(packed)
+    ev.close()
+    assert log[0] == "Filtered: 4 / 7" and res.CoverageR.shape == (4, 30) and res.MatchingP.shape == (4,)
+    for k, mol in enumerate(mols):
+        n = mol.num_nodes
+        heavy = np.nonzero(np.asarray(mol.atom_type) > 1)[0]
+        ref = packed[k]["pos_ref"].reshape(-1, n, 3).numpy()
+        gen = packed[k]["pos_gen"].reshape(-1, n, 3).numpy()[: 2 * ref.shape[0]]
+        conf = K.rmsd_confusion_matrix(ref, gen, heavy)
+        # thresholds sit on a 0.05 grid: compare the coverage only where no RMSD is within 1e-4 of a threshold
+        cov_r, mat_r, cov_p, mat_p = K.covmat_scores(conf, ev.thresholds)
+        safe_r = np.array([np.abs(conf.min(-1) - t).min() > 1e-4 for t in ev.thresholds])
+        safe_p = np.array([np.abs(conf.min(0) - t).min() > 1e-4 for t in ev.thresholds])
+        assert np.array_equal(res.CoverageR[k][safe_r], cov_r[safe_r]) and np.array_equal(res.CoverageP[k][safe_p], cov_p[safe_p])
+        assert abs(res.MatchingR[k] - mat_r) <= 2e-5 and abs(res.MatchingP[k] - mat_p) <= 2e-5
+    c, m_ = evaluation.evaluate_conf(packed[2], threshold=0.5)
+    conf = K.rmsd_confusion_matrix(packed[2]["pos_ref"].reshape(-1, mols[2].num_nodes, 3).numpy(),
+                                   packed[2]["pos_gen"].reshape(-1, mols[2].num_nodes, 3).numpy(), np.nonzero(np.asarray(mols[2].atom_type) > 1)[0])
+    assert abs(m_ - conf.min(-1).mean()) <= 2e-5 and abs(c - (conf.min(-1) <= 0.5).mean()) <= 1e-12
+    rows = evaluation.print_covmat_results(res, print_fn=lambda s_: None)
+    assert len(rows) == 31

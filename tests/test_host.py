@@ -309,3 +309,30 @@ def test_fp16_split_arithmetic_model(ascale):
         assert err0 > 10 * err                                 # subnormal lo parts: visibly worse
     else:
         assert err0 < 1e-6
+
+
+def test_kabsch_oracle_properties():
+    """the COV/MAT oracle itself: invariance under proper rigid motion, no alignment of mirror images, the closed form for a
+    pure scaling, symmetry of the matrix for identical sets, and the COV/MAT bookkeeping of covmat.py:131-150"""
+    from oracle import kabsch_oracle as K
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=(30, 3))
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    q *= np.sign(np.linalg.det(q))
+    assert K.kabsch_rmsd(a, a @ q.T + 3.0) < 1e-7
+    assert K.kabsch_rmsd(a, a * np.array([1.0, 1.0, -1.0])) > 0.1
+    a0 = a - a.mean(0)
+    assert abs(K.kabsch_rmsd(a, 1.5 * a) - 0.5 * np.sqrt((a0 ** 2).sum() / 30)) < 1e-9
+    confs = rng.normal(size=(4, 30, 3))
+    m = K.rmsd_confusion_matrix(confs, confs)
+    assert np.allclose(m, m.T, atol=1e-9) and np.abs(np.diag(m)).max() < 1e-7
+    conf = np.array([[0.1, 0.9], [0.6, 0.4], [2.0, 3.0]])
+    cov_r, mat_r, cov_p, mat_p = K.covmat_scores(conf, np.array([0.5, 1.0]))
+    assert np.allclose(cov_r, [2 / 3, 2 / 3]) and abs(mat_r - (0.1 + 0.4 + 2.0) / 3) < 1e-12
+    assert np.allclose(cov_p, [1.0, 1.0]) and abs(mat_p - 0.25) < 1e-12
+
+
+def test_evaluation_has_no_cpu_path():
+    from agdiff_b200 import evaluation
+    with pytest.raises(RuntimeError):
+        evaluation.rmsd_matrix(np.zeros((1, 4, 3)), np.zeros((1, 4, 3)), device="cpu")

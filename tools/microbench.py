@@ -56,7 +56,7 @@ for E in (100_000, 300_000, 1_000_000, 3_000_000, 10_000_000):
         out = torch.empty(N, F, device=dev)
         t = timeit(lambda: _lib.check(lib.agd_op_cfconv_aggregate(P(x), P(W), P(src), P(in_ptr), N, F, P(out), st)))
         byts = E * (4 * F + 4 * F + 4) + N * (4 * F + 4)
-        rows.append(("cfconv_aggregate F=%d" % F, E, t * 1e6, byts / t / 1e9))
+        rows.append(("cfconv_aggregate F=%d" % F, E, t * 1e6, byts / t / 1e9, (E * (4 * F + 4) + N * (8 * F + 4)) / t / 1e9))
         del x, W, out
     pos = torch.randn(N, 3, generator=gen).to(dev)
     dst = torch.arange(N, dtype=torch.int32).repeat_interleave(32).to(dev)
@@ -65,7 +65,7 @@ for E in (100_000, 300_000, 1_000_000, 3_000_000, 10_000_000):
     out = torch.empty(N, 3, device=dev)
     t = timeit(lambda: _lib.check(lib.agd_op_eq_transform(P(sc), P(pos), P(src), P(dst), P(ln), E, N, P(out), st)))
     byts = E * (4 + 8 + 4 + 24) + N * 24
-    rows.append(("eq_transform (atomics)", E, t * 1e6, byts / t / 1e9))
+    rows.append(("eq_transform (atomics)", E, t * 1e6, byts / t / 1e9, (E * 16 + N * 24) / t / 1e9))
     # (iii b) the same edge list as sorted segments: CSC as built (sorted by col = dst) and re-sorted by row for the out-segments
     order = torch.argsort(src.long(), stable=True)
     col_of_out = dst[order].contiguous()
@@ -73,7 +73,7 @@ for E in (100_000, 300_000, 1_000_000, 3_000_000, 10_000_000):
     sc_out = sc[order].contiguous()
     t = timeit(lambda: _lib.check(lib.agd_op_eq_transform_segments(P(pos), P(sc_out), P(col_of_out), P(out_ptr), P(sc), P(src), P(in_ptr), N, P(out), st)))
     byts = 2 * E * (4 + 4 + 12) + N * (12 + 8 + 12)   # every edge is visited from both ends: score + index + the far position
-    rows.append(("eq_transform (segments)", E, t * 1e6, byts / t / 1e9))
+    rows.append(("eq_transform (segments)", E, t * 1e6, byts / t / 1e9, (2 * E * 8 + N * 32) / t / 1e9))
     del order, col_of_out, out_ptr, sc_out
     # (ii) GIN message
     x = (torch.rand(N, 128, generator=gen) * 2 - 1).to(dev)
@@ -81,10 +81,12 @@ for E in (100_000, 300_000, 1_000_000, 3_000_000, 10_000_000):
     o = torch.empty(N, 128, device=dev)
     t = timeit(lambda: _lib.check(lib.agd_op_gin_message(P(x), P(ea), P(src), P(in_ptr), N, C.c_float(0.1), P(o), st)))
     byts = E * (512 + 512 + 4) + N * (512 + 512 + 4)
-    rows.append(("gin_message", E, t * 1e6, byts / t / 1e9))
+    rows.append(("gin_message", E, t * 1e6, byts / t / 1e9, (E * 516 + N * 1028) / t / 1e9))
     del x, ea, o
 
-print("| kernel | edges | us/launch | algorithmic GB/s | frac of measured HBM peak (%.0f GB/s) |" % peak)
-print("|---|---|---|---|---|")
-for name, E, us, gbs in rows:
-    print("| %s | %d | %.1f | %.0f | %.2f |" % (name, E, us, gbs, gbs / peak))
+# algorithmic: SURVEY 8d's bytes (the gathered operand counted per edge - with N = E/32 it is served by L2, so this is a mixed
+# HBM + L2 rate); compulsory: edge stream + indices + the gathered table once + the output, as a fraction of the measured HBM peak
+print("| kernel | edges | us/launch | algorithmic GB/s | compulsory HBM GB/s | frac of measured HBM peak (%.0f GB/s) |" % peak)
+print("|---|---|---|---|---|---|")
+for name, E, us, gbs, comp in rows:
+    print("| %s | %d | %.1f | %.0f | %.0f | %.2f |" % (name, E, us, gbs, comp, comp / peak))
