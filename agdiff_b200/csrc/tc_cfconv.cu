@@ -516,16 +516,20 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
     asm volatile("" : "+r"(first_), "+r"(e_)); /* opaque: keeps ptxas from parking pass-invariant indices on the stack */ \
     _Pragma("unroll") for (int u = 0; u < CF_STEPS; ++u) {                                                           \
       const int rr = first_ + 4 * u;                                                                                 \
-      xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);                                                                       \
       if (rr < e_) xv[u] = __ldg(reinterpret_cast<const float4*>(px_ + (bsrc_)[rr]));                                \
     }                                                                                                                \
   }
+  // Steps past the end of the run are never loaded, so their x stays what CF_ZERO_X made it when the warp took the run over:
+  // zero once per tile instead of once per pass (and never a stale value of another run, i.e. of another molecule).
+#define CF_ZERO_X() \
+  { _Pragma("unroll") for (int u = 0; u < CF_STEPS; ++u) xv[u] = make_float4(0.f, 0.f, 0.f, 0.f); }
     const uint32_t full = bar0 + 8 * (B_FULL0 + team), empty = bar0 + 8 * (B_EMPTY0 + team);
     const float* sw = s_W + team * (TM * LDS_Q) + c4;   // the team's slab
     uint32_t n_use = 0;
     if (T > 0) {
       mbar_wait_s(bar0 + 8 * B_BK_FULL0, 0u);
       cur = item_of(rw, 0);
+      CF_ZERO_X();
       CF_REQUEST(cur, s_bk, 32 * team + c4);
     }
     for (int j = 0; j < T; ++j) {
@@ -573,6 +577,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
           mbar_wait_s(bar0 + 8 * (B_BK_FULL0 + ((j + 1) & 1)), static_cast<uint32_t>((j + 1) >> 1) & 1u);
           cur = item_of(rw, j + 1);
           const int* bsrc_n = s_bk + ((j + 1) & 1) * CF_BKS;
+          CF_ZERO_X();
           CF_REQUEST(cur, bsrc_n, 32 * team + c4);
         }
         pc.tick(3);
@@ -581,6 +586,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
       if (lane == 0) mbar_arrive_s(bar0 + 8 * (B_BK_FREE0 + (j & 1)));
     }
 #undef CF_REQUEST
+#undef CF_ZERO_X
     pc.flush(a.timing, 2);
     } else if (warp == CF_WARP_M && T > 0) {
     // ================================================================== M: weights + MMA issue (warp-uniform, elect inside)

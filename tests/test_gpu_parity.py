@@ -439,6 +439,30 @@ def test_f16_fused_aggregation_bitwise_equals_unfused(kind, cfg_name, scale, rep
     assert torch.equal(rf[0], ru[0]) and torch.equal(rf[1], ru[1])
 
 
+def test_fused_aggregation_stress_random_tilings():
+    """Race / hand-off stress for the warp-specialised CFConv kernel (slab ring, carry buffer, bookkeeping ring are all
+    mbarrier-guarded, which compute-sanitizer's racecheck does not model: profiles/r02_sanitizer.md).  Twelve batches of random
+    size and density - run lengths, tile boundaries and CTA ranges fall differently every time -, each evaluated twice fused and
+    once unfused: all three aggregates must be bit-identical."""
+    m, sd = _cuda_model("drugs", 2021, 5)
+    _settle(m)
+    rng = np.random.default_rng(17)
+    for it in range(12):
+        n_mols = int(rng.integers(3, 40))
+        mols = [graph.extend_bond_order_host(x) for x in synth.drugs_like(n_mols, seed=100 + it, force_max=bool(it % 3 == 0))]
+        z, bi, bt, b, G = graph.collate(mols, int(rng.integers(1, 4)))
+        pos = torch.randn(z.numel(), 3, generator=torch.Generator().manual_seed(it)) * float(rng.uniform(1.0, 6.0))
+        m.set_option("f16_fuse", 1)
+        r1, i1 = _fwd_mode(m, 2, z, pos, bi, bt, b, fetch=("agg",))
+        r2, i2 = _fwd_mode(m, 2, z, pos, bi, bt, b, fetch=("agg",))
+        m.set_option("f16_fuse", 0)
+        r3, i3 = _fwd_mode(m, 2, z, pos, bi, bt, b, fetch=("agg",))
+        m.set_option("f16_fuse", 1)
+        assert torch.equal(i1["agg"], i2["agg"]), "fused kernel not reproducible (iteration %d)" % it
+        assert torch.equal(i1["agg"], i3["agg"]), "fused != unfused (iteration %d, %d atoms)" % (it, z.numel())
+        assert torch.equal(r1[0], r3[0]) and torch.equal(r1[1], r3[1])
+
+
 def test_f16_range_overflow_falls_back_to_tf32():
     """activations beyond the fp16 range: the fp16-split kernels flag it and the host re-runs the call on the 3xTF32
     kernels, so the result equals the 3xTF32 result bit for bit (forward and sampler)."""
