@@ -64,6 +64,50 @@ constexpr int F16_GROUP = 256;
 constexpr int F16_GWARPS = 8;
 constexpr int SLOT_COLS = 256;          // TMEM columns per slot
 constexpr int C16_D = 0, C16_AHI = 128, C16_ALO = 192;
+// one lane of a converged warp (the MMA issue below runs inside `if (elect_one())`: with a warp-uniform branch and compile-time
+// TMEM addresses an MMA costs ~6 instructions; issued by a single thread of a diverged warp with run-time addresses it costs
+// ~12 plus a uniform-branch loop per instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t el;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(el));
+  return el != 0;
+}
+
+// The same layers with the slot's TMEM columns as a template parameter (the kernel owns all 512 columns: the allocation starts
+// at column 0, checked by the callers) - to be called by one elected lane.
+template <int K, int N, uint32_t SLOT>
+__device__ __forceinline__ void issue_3xf16_ct(uint32_t w_smem, uint32_t half_bytes, bool scaled) {
+  constexpr uint32_t idesc = tc::idesc_f16(N);
+  constexpr uint32_t D = SLOT + C16_D, ahi = SLOT + C16_AHI, alo = SLOT + C16_ALO;
+  const uint64_t d_hi = tc::smem_desc_sw128(w_smem), d_lo = d_hi + (half_bytes >> 4);
+#pragma unroll
+  for (int kb = 0; kb < K / 16; ++kb) {
+    const uint32_t boff16 = (static_cast<uint32_t>(kb >> 2) * (N * 128) + static_cast<uint32_t>(kb & 3) * 32) >> 4;
+    tc::mma_f16_ts(D, ahi + kb * 8, d_lo + boff16, idesc, kb > 0 ? 1u : 0u);
+    tc::mma_f16_ts(D, alo + kb * 8, d_hi + boff16, idesc, 1u);
+  }
+  if (scaled) tc::mma_f16_ts_scaled<F16_LO_SHIFT>(D, ahi, d_hi, idesc);
+  else tc::mma_f16_ts(D, ahi, d_hi, idesc, 1u);
+#pragma unroll
+  for (int kb = 1; kb < K / 16; ++kb) {
+    const uint32_t boff16 = (static_cast<uint32_t>(kb >> 2) * (N * 128) + static_cast<uint32_t>(kb & 3) * 32) >> 4;
+    tc::mma_f16_ts(D, ahi + kb * 8, d_hi + boff16, idesc, 1u);
+  }
+}
+template <int K, int N, uint32_t SLOT>
+__device__ __forceinline__ void issue_3xf16_acc_ct(uint32_t w_smem, uint32_t half_bytes) {
+  constexpr uint32_t idesc = tc::idesc_f16(N);
+  constexpr uint32_t D = SLOT + C16_D, ahi = SLOT + C16_AHI, alo = SLOT + C16_ALO;
+  const uint64_t d_hi = tc::smem_desc_sw128(w_smem), d_lo = d_hi + (half_bytes >> 4);
+#pragma unroll
+  for (int kb = 0; kb < K / 16; ++kb) {
+    const uint32_t boff16 = (static_cast<uint32_t>(kb >> 2) * (N * 128) + static_cast<uint32_t>(kb & 3) * 32) >> 4;
+    tc::mma_f16_ts(D, ahi + kb * 8, d_lo + boff16, idesc, 1u);
+    tc::mma_f16_ts(D, alo + kb * 8, d_hi + boff16, idesc, 1u);
+    tc::mma_f16_ts(D, ahi + kb * 8, d_hi + boff16, idesc, 1u);
+  }
+}
+
 // the 3 x K/16 MMAs of one layer for one slot, issued by ONE thread: cross terms first, then the main chain
 template <int K, int N>
 __device__ __forceinline__ void issue_3xf16(uint32_t slot, uint32_t w_smem, uint32_t half_bytes, bool scaled) {

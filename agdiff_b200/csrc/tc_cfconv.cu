@@ -116,13 +116,8 @@ __device__ __forceinline__ void mma_commit_s(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// ---- MMA issue: one elected lane of the (converged) MMA warp runs a whole layer; the other lanes skip it
-__device__ __forceinline__ bool elect_one() {
-  uint32_t el;
-  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(el));
-  return el != 0;
-}
-// clock64 phase accounting of one observer lane per role (diagnostics only: tools/phase_timing.py)
+// ---- MMA issue: one elected lane of the (converged) MMA warp runs a whole layer; the other lanes skip it (elect_one: tc16_common.cuh)
+
 struct PhaseClock {
 #ifdef AGD_F16_TIMING
   long long t_prev;

@@ -24,7 +24,7 @@ struct Slot16 {
   uint32_t slot, trow;
   uint64_t *a_ready, *d_ready;
   uint32_t dph, aph;
-  bool issuer, scaled;
+  bool issuer, scaled;   // issuer: this thread's WARP issues the group's MMAs (one elected lane)
 
   // this thread's operand stores are done: publish them, (issuer) run one layer on the tensor core
   template <int K, int N>
@@ -32,11 +32,15 @@ struct Slot16 {
     wait_st();
     fence_before_sync();
     mbar_arrive(a_ready);
-    if (issuer) {
+    if (issuer) {   // warp-uniform: the group's first warp
       mbar_wait(a_ready, aph);
       fence_after_sync();
-      issue_3xf16<K, N>(slot, w_smem, half_bytes, scaled);
-      mma_commit(d_ready);
+      if (elect_one()) {
+        if (slot == 0u) issue_3xf16_ct<K, N, 0u>(w_smem, half_bytes, scaled);
+        else issue_3xf16_ct<K, N, SLOT_COLS>(w_smem, half_bytes, scaled);
+        mma_commit(d_ready);
+      }
+      __syncwarp();
     }
     aph ^= 1u;
   }
@@ -119,6 +123,12 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_encoder16_kernel(const TcEn
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *s_tmem;
+  if (tmem != 0u) {   // the MMA issue uses compile-time TMEM addresses: the allocation of all 512 columns must start at column 0
+    if (tid == 0) atomicOr(a.range_flag, 2);   // (cannot happen with one CTA per SM; if it ever does, the host re-runs in mode 1)
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+    return;
+  }
 
   if (tid == 0 && static_cast<int>(blockIdx.x) * 2 < n_tiles) {   // all weight images, once
     mbar_expect_tx(&bars[0], (LOCAL ? 3 : 2) * IMG16_128);
@@ -138,7 +148,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_encoder16_kernel(const TcEn
     sl.d_ready = &bars[3 + g];
     sl.dph = 0;
     sl.aph = 0;
-    sl.issuer = (tid & (F16_GROUP - 1)) == 0;
+    sl.issuer = (warp & (F16_GWARPS - 1)) == 0;
     sl.scaled = a.scaled != 0;
     const float inv1 = __ldg(a.wsc + 0), inv2 = __ldg(a.wsc + 1), inv3 = __ldg(a.wsc + 2);
     const float lo_scale = a.scaled ? static_cast<float>(1 << F16_LO_SHIFT) : 1.0f;
@@ -368,6 +378,12 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_pair16_kernel(const TcPair1
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *s_tmem;
+  if (tmem != 0u) {   // the MMA issue uses compile-time TMEM addresses: the allocation of all 512 columns must start at column 0
+    if (tid == 0) atomicOr(a.range_flag, 2);   // (cannot happen with one CTA per SM; if it ever does, the host re-runs in mode 1)
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+    return;
+  }
 
   if (tid == 0 && static_cast<int>(blockIdx.x) * 2 < n_tiles) {   // all weight images, once
     mbar_expect_tx(&bars[0], 2 * IMG16_128 + IMG16_64);
@@ -387,7 +403,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_pair16_kernel(const TcPair1
     sl.d_ready = &bars[3 + g];
     sl.dph = 0;
     sl.aph = 0;
-    sl.issuer = (tid & (F16_GROUP - 1)) == 0;
+    sl.issuer = (warp & (F16_GWARPS - 1)) == 0;
     sl.scaled = a.scaled != 0;
     const float inv1 = __ldg(a.wsc + 0), inv2 = __ldg(a.wsc + 2);
     const float lo_scale = a.scaled ? static_cast<float>(1 << F16_LO_SHIFT) : 1.0f;
@@ -523,8 +539,12 @@ __global__ void __launch_bounds__(F16_THREADS, 1) tc_pair16_kernel(const TcPair1
         if (sl.issuer) {
           mbar_wait(sl.a_ready, sl.aph);
           fence_after_sync();
-          issue_3xf16_acc<HID, HID>(sl.slot, smem_u32(wP1e), IMG16_128 / 2);   // layers.0, edge half, accumulated
-          mma_commit(sl.d_ready);
+          if (elect_one()) {
+            if (sl.slot == 0u) issue_3xf16_acc_ct<HID, HID, 0u>(smem_u32(wP1e), IMG16_128 / 2);   // layers.0, edge half, accumulated
+            else issue_3xf16_acc_ct<HID, HID, SLOT_COLS>(smem_u32(wP1e), IMG16_128 / 2);
+            mma_commit(sl.d_ready);
+          }
+          __syncwarp();
         }
         sl.aph ^= 1u;
       }

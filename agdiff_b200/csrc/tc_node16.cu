@@ -76,11 +76,14 @@ struct Node16Ctx {
     fence_before_sync();
     __syncthreads();
     const int b = n_layers & 1;
-    if (tid == 0) {
+    if (tid < 32) {   // warp 0 (converged): waits for the layer's weights, one elected lane issues the layer
       fence_after_sync();
       mbar_wait(&bars[b], wph[b]);
-      issue_3xf16<K, N>(tmem, smem_u32(wbuf[b]), static_cast<uint32_t>(K) * N * 2u, scaled);
-      mma_commit(&bars[2]);
+      if (elect_one()) {
+        issue_3xf16_ct<K, N, 0u>(smem_u32(wbuf[b]), static_cast<uint32_t>(K) * N * 2u, scaled);
+        mma_commit(&bars[2]);
+      }
+      __syncwarp();
     }
     wph[b] ^= 1u;
     ++n_layers;
@@ -160,6 +163,12 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
   fence_after_sync();
   Node16Ctx cx;
   cx.wbuf[0] = base; cx.wbuf[1] = base + NIMG_128; cx.bars = bars; cx.tmem = *s_tmem;
+  if (cx.tmem != 0u) {   // the MMA issue uses compile-time TMEM addresses: this CTA is alone on its SM, so the allocation starts at 0
+    if (tid == 0) atomicOr(a.range_flag, 2);   // (if it ever does not, the host re-runs the call in mode 1)
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(cx.tmem, 256);
+    return;
+  }
   cx.trow = cx.tmem + (static_cast<uint32_t>(quad * 32) << 16);
   cx.wph[0] = cx.wph[1] = 0; cx.m_phase = 0; cx.tid = tid; cx.n_streamed = 0; cx.n_layers = 0;
   cx.scaled = a.scaled != 0;
