@@ -98,40 +98,44 @@ __global__ void __launch_bounds__(STEP_THREADS) langevin_step_kernel(const StepA
     const float px = pos[3 * (size_t)at], py = pos[3 * (size_t)at + 1], pz = pos[3 * (size_t)at + 2];
     float vx = 0.f, vy = 0.f, vz = 0.f;
     if (active) {
-      if (part == 0) {          // local, atom is edge_index[1]: subtract
-        for (int e = a.lin_ptr[at]; e < a.lin_ptr[at + 1]; ++e) {
-          const int s = a.lsrc[e];
-          const float inv = 1.0f / a.llen[e], sc = a.sl_csc[e];
-          vx -= (inv * (pos[3 * (size_t)s] - px)) * sc;
-          vy -= (inv * (pos[3 * (size_t)s + 1] - py)) * sc;
-          vz -= (inv * (pos[3 * (size_t)s + 2] - pz)) * sc;
+      // Each part walks one sorted segment.  The walk is latency-bound (index -> position, two dependent L2 round trips per
+      // edge), so edges are taken four at a time: all loads of a batch are issued before the first use, the sum is then
+      // accumulated edge by edge in segment order - the same arithmetic in the same order as a one-edge-at-a-time loop.
+      const int* ptr = (part == 0) ? a.lin_ptr : (part == 1) ? a.lout_ptr : (part == 2) ? a.in_ptr : a.out_ptr;
+      const int* other = (part == 0) ? a.lsrc : (part == 1) ? a.lcdst : (part == 2) ? a.e_src : a.c_dst;
+      const float* elen = (part == 0) ? a.llen : (part == 1) ? a.lclen : (part == 2) ? a.e_len : a.c_len;
+      const float* esc = (part == 0) ? a.sl_csc : (part == 1) ? a.sl_canon : (part == 2) ? a.s_csc : a.s_canon;
+      const int* etype = (part == 2) ? a.e_type : (part == 3) ? a.c_type : nullptr;   // global parts skip the local edges (type > 0)
+      const bool in_seg = (part & 1) == 0;   // in-segments: the atom is edge_index[1] -> subtract (pos[src] - p); out-segments: add (p - pos[dst])
+      const int e0 = (part < 2 || a.p.use_global) ? ptr[at] : 0, e1 = (part < 2 || a.p.use_global) ? ptr[at + 1] : 0;
+      for (int e = e0; e < e1; e += 4) {
+        int j[4];
+        float inv[4], sc[4], qx[4], qy[4], qz[4];
+        bool use[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ee = (e + u < e1) ? e + u : e1 - 1;
+          use[u] = (e + u < e1) && !(etype && etype[ee] > 0);
+          j[u] = other[ee];
+          inv[u] = elen[ee];
+          sc[u] = esc[ee];
         }
-      } else if (part == 1) {   // local, atom is edge_index[0]: add
-        for (int c = a.lout_ptr[at]; c < a.lout_ptr[at + 1]; ++c) {
-          const int t = a.lcdst[c];
-          const float inv = 1.0f / a.lclen[c], sc = a.sl_canon[c];
-          vx += (inv * (px - pos[3 * (size_t)t])) * sc;
-          vy += (inv * (py - pos[3 * (size_t)t + 1])) * sc;
-          vz += (inv * (pz - pos[3 * (size_t)t + 2])) * sc;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          qx[u] = pos[3 * (size_t)j[u]]; qy[u] = pos[3 * (size_t)j[u] + 1]; qz[u] = pos[3 * (size_t)j[u] + 2];
         }
-      } else if (a.p.use_global) {
-        if (part == 2) {        // global: edge_inv_global * (1 - local_mask), in-edges
-          for (int e = a.in_ptr[at]; e < a.in_ptr[at + 1]; ++e) {
-            if (a.e_type[e] > 0) continue;
-            const int s = a.e_src[e];
-            const float inv = 1.0f / a.e_len[e], sc = a.s_csc[e];
-            vx -= (inv * (pos[3 * (size_t)s] - px)) * sc;
-            vy -= (inv * (pos[3 * (size_t)s + 1] - py)) * sc;
-            vz -= (inv * (pos[3 * (size_t)s + 2] - pz)) * sc;
-          }
-        } else {                // global, out-edges
-          for (int c = a.out_ptr[at]; c < a.out_ptr[at + 1]; ++c) {
-            if (a.c_type[c] > 0) continue;
-            const int t = a.c_dst[c];
-            const float inv = 1.0f / a.c_len[c], sc = a.s_canon[c];
-            vx += (inv * (px - pos[3 * (size_t)t])) * sc;
-            vy += (inv * (py - pos[3 * (size_t)t + 1])) * sc;
-            vz += (inv * (pz - pos[3 * (size_t)t + 2])) * sc;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!use[u]) continue;
+          const float iv = 1.0f / inv[u];
+          if (in_seg) {
+            vx -= (iv * (qx[u] - px)) * sc[u];
+            vy -= (iv * (qy[u] - py)) * sc[u];
+            vz -= (iv * (qz[u] - pz)) * sc[u];
+          } else {
+            vx += (iv * (px - qx[u])) * sc[u];
+            vy += (iv * (py - qy[u])) * sc[u];
+            vz += (iv * (pz - qz[u])) * sc[u];
           }
         }
       }
