@@ -188,6 +188,24 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t tmem, uint32_t b_smem, boo
   }
 }
 
+// The same layer with the TMEM base as a compile-time 0 (a kernel that owns all 512 columns), to be called by ONE elected lane
+// of a converged warp (tc16_common.cuh: elect_one): half the issue instructions of the single-diverged-thread form above.
+template <int K, int N, bool SPLIT>
+__device__ __forceinline__ void issue_3xtf32_ct(uint32_t b_smem, bool accumulate) {
+  constexpr uint32_t idesc = tc::idesc_tf32(N);
+  constexpr uint32_t half_bytes = static_cast<uint32_t>(K) * N * 4;
+  const uint64_t d_hi = tc::smem_desc_sw128(b_smem), d_lo = d_hi + (half_bytes >> 4);
+  constexpr uint32_t dmain = tc::COL_D, dx = SPLIT ? tc::COL_D2 : tc::COL_D;
+#pragma unroll
+  for (int kb = 0; kb < K / 8; ++kb) {
+    const uint32_t boff16 = (static_cast<uint32_t>(kb >> 2) * (N * 128) + static_cast<uint32_t>(kb & 3) * 32) >> 4;
+    const uint32_t acc = (accumulate || kb > 0) ? 1u : 0u;
+    tc::mma_tf32_ts(dmain, tc::COL_AHI + kb * 8, d_hi + boff16, idesc, acc);
+    tc::mma_tf32_ts(dx, tc::COL_AHI + kb * 8, d_lo + boff16, idesc, SPLIT ? acc : 1u);
+    tc::mma_tf32_ts(dx, tc::COL_ALO + kb * 8, d_hi + boff16, idesc, 1u);
+  }
+}
+
 // split an fp32 value into two TF32 values with round-to-nearest: hi = rna(v), lo = rna(v - hi) (v - hi is exact).
 // |v - (hi + lo)| <= 2^-22 |v| and unbiased; feeding raw fp32 bits instead would let the tensor core TRUNCATE
 // (2^-20, biased), which the far-geometry parity case does not tolerate.

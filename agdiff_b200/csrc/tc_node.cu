@@ -33,6 +33,12 @@ struct TcNodeArgs {
 
 constexpr size_t TC_NODE_SMEM = 1024 + 131072 + (128 * 3 + 64 * 2 + 128 + 64 + 1024 + 1024 + 512 + 4096) * sizeof(float) + 256;
 
+__device__ __forceinline__ bool elect_one_tf32() {
+  uint32_t el;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(el));
+  return el != 0;
+}
+
 struct NodeCtx {   // TcCtx from tc_mlp.cu, repeated here to keep the translation units independent
   uint8_t* wbuf;
   uint64_t* bars;
@@ -56,6 +62,26 @@ struct NodeCtx {   // TcCtx from tc_mlp.cu, repeated here to keep the translatio
       else if (K == 64 && N == 128) issue_3xtf32<64, 128, true>(tmem, b_smem, false);
       else issue_3xtf32<128, 64, true>(tmem, b_smem, false);
       mma_commit(&bars[1]);
+    }
+    w_phase ^= 1;
+    mbar_wait(&bars[1], m_phase);
+    m_phase ^= 1;
+    fence_after_sync();
+  }
+  // 128 x 128 layer issued by one elected lane of warp 0 with compile-time TMEM addresses (only valid when the kernel's TMEM
+  // allocation starts at column 0 - the caller checks)
+  __device__ __forceinline__ void layer128_elected() {
+    wait_st();
+    fence_before_sync();
+    __syncthreads();
+    if (tid < 32) {
+      fence_after_sync();
+      mbar_wait(&bars[0], w_phase);
+      if (elect_one_tf32()) {
+        issue_3xtf32_ct<128, 128, true>(smem_u32(wbuf), false);
+        mma_commit(&bars[1]);
+      }
+      __syncwarp();
     }
     w_phase ^= 1;
     mbar_wait(&bars[1], m_phase);
@@ -401,6 +427,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
   fence_after_sync();
   NodeCtx cx;
   cx.wbuf = base; cx.bars = bars; cx.tmem = *s_tmem;
+  const bool tmem_at_0 = cx.tmem == 0u;   // always, for the SM's only CTA allocating all 512 columns: the elected-lane issue relies on it
   cx.trow = cx.tmem + (static_cast<uint32_t>(quad * 32) << 16);
   cx.w_phase = 0; cx.m_phase = 0; cx.tid = tid;
   const float ope = __ldg(a.w.sc);
@@ -475,7 +502,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
     }
     GIN_TICK(3);   // lift into TMEM
   
-    cx.layer(128, 128);
+    if (tmem_at_0) cx.layer128_elected(); else cx.layer(128, 128);
     GIN_TICK(4);   // layer 1
     if (tid == 0) cx.stream(a.tG2, IMG);
 #pragma unroll
@@ -488,7 +515,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tc_gin_kernel(const TcGinArgs 
       st_split16(cx.trow, n0, t);
     }
     GIN_TICK(5);   // epilogue 1
-    cx.layer(128, 128);
+    if (tmem_at_0) cx.layer128_elected(); else cx.layer(128, 128);
     GIN_TICK(6);   // layer 2
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
