@@ -539,7 +539,11 @@ __global__ void __launch_bounds__(CF_THREADS, 1) tc_cfconv_kernel(const CfArgs a
         const float* carry_r = s_carry + ((j & 1) ^ 1) * 768 + rq * 192 + col;
         mbar_wait_s(full, n_use & 1u);
         pc.tick(1);
-        if (rw < n_runs && !(a.debug_filt & 4)) {
+        // (opaque copy: evaluated before the wait, the condition below becomes a predicate that ptxas saves to the stack across
+        // the wait loop and reloads right behind it - an L2 round trip in front of every consume: 300 k local loads per launch)
+        int n_runs_ = n_runs;
+        asm volatile("" : "+r"(n_runs_));
+        if (rw < n_runs_ && !(a.debug_filt & 4)) {
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           if (cur.cin) acc = *reinterpret_cast<const float4*>(carry_r);
           // (opaque copies: the twelve row indices below are pass-invariant, and ptxas would rather keep them on the stack across

@@ -54,10 +54,12 @@ struct TcNode16Args {
 constexpr size_t TC_NODE16_SMEM = 1024 + 2 * NIMG_128 + (128 * 3 + 64 * 2 + 128 + 64 + 1024 + 1024 + 512 + 4096) * sizeof(float) + 256;
 
 struct Node16Ctx {
-  uint8_t* wbuf[2];
+  // (no arrays indexed by a run-time value in here: they would put the whole struct into local memory - with ~70 KB of L1 left
+  // that is an L2 round trip for the phase bit and the buffer address in front of every layer's MMA issue)
+  uint8_t *wbuf0, *wbuf1;
   uint64_t* bars;      // [0], [1]: weights landed in buffer 0 / 1, [2]: mma done
   uint32_t tmem, trow;
-  uint32_t wph[2], m_phase;
+  uint32_t wph0, wph1, m_phase;
   int tid;
   int n_streamed, n_layers;   // running counters: layer i uses buffer i & 1
   bool scaled;
@@ -65,9 +67,10 @@ struct Node16Ctx {
   // request the image of the NEXT not-yet-requested layer (tid 0 only); the buffer's previous user completed two layers ago
   __device__ __forceinline__ void stream(const float* img, uint32_t bytes) {
     const int b = n_streamed & 1;
+    uint8_t* dst = b ? wbuf1 : wbuf0;
     mbar_expect_tx(&bars[b], bytes);
     const uint8_t* src = reinterpret_cast<const uint8_t*>(img);
-    for (uint32_t off = 0; off < bytes; off += 16384) bulk_g2s(wbuf[b] + off, src + off, 16384, &bars[b]);
+    for (uint32_t off = 0; off < bytes; off += 16384) bulk_g2s(dst + off, src + off, 16384, &bars[b]);
     ++n_streamed;
   }
   template <int K, int N>
@@ -78,14 +81,14 @@ struct Node16Ctx {
     const int b = n_layers & 1;
     if (tid < 32) {   // warp 0 (converged): waits for the layer's weights, one elected lane issues the layer
       fence_after_sync();
-      mbar_wait(&bars[b], wph[b]);
+      mbar_wait(&bars[b], b ? wph1 : wph0);
       if (elect_one()) {
-        issue_3xf16_ct<K, N, 0u>(smem_u32(wbuf[b]), static_cast<uint32_t>(K) * N * 2u, scaled);
+        issue_3xf16_ct<K, N, 0u>(smem_u32(b ? wbuf1 : wbuf0), static_cast<uint32_t>(K) * N * 2u, scaled);
         mma_commit(&bars[2]);
       }
       __syncwarp();
     }
-    wph[b] ^= 1u;
+    if (b) wph1 ^= 1u; else wph0 ^= 1u;
     ++n_layers;
     mbar_wait(&bars[2], m_phase);
     m_phase ^= 1u;
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
   __syncthreads();
   fence_after_sync();
   Node16Ctx cx;
-  cx.wbuf[0] = base; cx.wbuf[1] = base + NIMG_128; cx.bars = bars; cx.tmem = *s_tmem;
+  cx.wbuf0 = base; cx.wbuf1 = base + NIMG_128; cx.bars = bars; cx.tmem = *s_tmem;
   if (cx.tmem != 0u) {   // the MMA issue uses compile-time TMEM addresses: this CTA is alone on its SM, so the allocation starts at 0
     if (tid == 0) atomicOr(a.range_flag, 2);   // (if it ever does not, the host re-runs the call in mode 1)
     __syncthreads();
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(TCN16_THREADS, 1) tc_node16_kernel(const TcNod
     return;
   }
   cx.trow = cx.tmem + (static_cast<uint32_t>(quad * 32) << 16);
-  cx.wph[0] = cx.wph[1] = 0; cx.m_phase = 0; cx.tid = tid; cx.n_streamed = 0; cx.n_layers = 0;
+  cx.wph0 = cx.wph1 = 0; cx.m_phase = 0; cx.tid = tid; cx.n_streamed = 0; cx.n_layers = 0;
   cx.scaled = a.scaled != 0;
   const float beta_act = a.first ? 1.f : __ldg(a.w.sc + 2);
   const float a2b = a.first ? 0.f : __ldg(a.w.sc + 3);
