@@ -463,6 +463,38 @@ def test_fused_aggregation_stress_random_tilings():
         assert torch.equal(r1[0], r3[0]) and torch.equal(r1[1], r3[1])
 
 
+@pytest.mark.parametrize("mode", [2, 1, 0])
+def test_local_pairs_bitwise_equal_per_directed_edge(mode):
+    """Pair mode of the local branch (edge encoder + pair MLP once per undirected pair, api.cu: run_local_branch) against the
+    evaluation of every directed local edge, bit for bit, in all three arithmetic modes - on a symmetric bond graph and on one
+    with a few one-directional bonds (those edges are their own pairs)."""
+    m, sd = _cuda_model("drugs", 2021, 4)
+    _settle(m)
+    z, bi, bt, b, G, pos = _batch("drugs", seed=19, scale=2.0, repeats=2)
+    keep = torch.ones(bi.size(1), dtype=torch.bool)
+    keep[torch.arange(5, bi.size(1), 97)] = False          # drop one direction of a handful of static edges
+    for bi_, bt_ in ((bi, bt), (bi[:, keep], bt[keep])):
+        outs = []
+        for pairs in (1, 0):
+            m.set_option("local_pairs", pairs)
+            m.set_mode(mode)
+            m._renorm_embedding(z.to(DEV))
+            m._sync_weights()
+            nb = m._prepare(z.to(DEV), bi_.to(DEV), bt_.to(DEV), b.to(DEV), False)
+            try:
+                res = m._forward_native(nb, pos.to(DEV))
+                n_loc = res[1].numel()
+                ea = nb.fetch("ea_local", n_loc * 128).cpu()
+            finally:
+                nb.close()
+            outs.append((res[0].cpu(), res[1].cpu(), ea))
+        m.set_option("local_pairs", 1)
+        m.set_mode(2)
+        assert torch.equal(outs[0][2], outs[1][2]), "edge_attr of the local edges differs"
+        assert torch.equal(outs[0][1], outs[1][1]), "edge_inv_local differs"
+        assert torch.equal(outs[0][0], outs[1][0]), "edge_inv_global differs"
+
+
 def test_f16_range_overflow_falls_back_to_tf32():
     """activations beyond the fp16 range: the fp16-split kernels flag it and the host re-runs the call on the 3xTF32
     kernels, so the result equals the 3xTF32 result bit for bit (forward and sampler)."""
