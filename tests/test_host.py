@@ -173,14 +173,20 @@ def _gloo_worker(rank, world, port, q):
     n_tot = sum(m.num_nodes for m in mols) * 2
     pos0 = torch.arange(n_tot * 3, dtype=torch.float32).view(n_tot, 3)
 
+    torch.manual_seed(1000 + rank)            # the usual per-rank seeding: the noise seed must NOT follow it
+    seen = {}
+
     def fake_sampler(z, pos, bi, bt, b, G, mol_gid=None, return_traj=False, **kw):
         # stands in for the CUDA sampler: depends on the rows it is given and on the global conformer id
         assert mol_gid.numel() == G and int(b.max()) + 1 == G
+        seen["seed"] = kw.get("seed")
         return pos * 2.0 + mol_gid[b].view(-1, 1).float(), []
 
     out = sample_sharded(fake_sampler, mols, 2, pos0, "cpu")
+    seeds = [None] * world
+    dist.all_gather_object(seeds, seen.get("seed"))
     if rank == 0:
-        q.put(out)
+        q.put((out, seeds))
     dist.destroy_process_group()
 
 
@@ -192,10 +198,11 @@ def test_sharded_sampling_world_size_2_gloo():
     procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    out = q.get(timeout=120)
+    out, seeds = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    assert seeds[0] is not None and seeds[0] == seeds[1]      # rank 0's seed was broadcast: results do not depend on the rank count
     mols = [graph.extend_bond_order_host(m) for m in synth.qm9_like(7, seed=3)]
     n_tot = sum(m.num_nodes for m in mols) * 2
     pos0 = torch.arange(n_tot * 3, dtype=torch.float32).view(n_tot, 3)
