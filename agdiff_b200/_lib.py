@@ -21,7 +21,7 @@ EXPORTS = [
     "agd_abi_version", "agd_last_error", "agd_create", "agd_destroy", "agd_weight_slot_count",
     "agd_weight_slot_name", "agd_weight_slot_size", "agd_load_weights", "agd_batch_workspace_bytes",
     "agd_batch_create", "agd_batch_destroy", "agd_build_edges", "agd_forward", "agd_sample",
-    "agd_extend_bond_order", "agd_op_cfconv_aggregate", "agd_op_eq_transform", "agd_op_gin_message", "agd_op_eq_transform_segments", "agd_op_kabsch_rmsd",
+    "agd_extend_bond_order", "agd_op_cfconv_aggregate", "agd_op_eq_transform", "agd_op_gin_message", "agd_op_eq_transform_segments", "agd_op_kabsch_rmsd", "agd_host_local_pairs",
     "agd_debug_fetch",
     "agd_launch_count", "agd_profile_forward", "agd_forward_edges",
     "agd_nan_steps", "agd_set_mode", "agd_get_mode", "agd_set_option", "agd_range_flag", "agd_f16_lo_shift", "agd_debug_timing",
@@ -110,6 +110,7 @@ def load() -> C.CDLL:
     lib.agd_op_gin_message.argtypes = [vp, vp, vp, vp, i32, C.c_float, vp, vp]
     lib.agd_op_eq_transform_segments.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
     lib.agd_op_kabsch_rmsd.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.agd_host_local_pairs.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     lib.agd_debug_fetch.argtypes = [vp, C.c_char_p, vp, i64]
     lib.agd_debug_fetch.restype = i64
     lib.agd_profile_forward.argtypes = [vp, vp, vp, i32, C.c_char_p, i64, vp, i32, C.POINTER(i32), C.POINTER(i32), vp]

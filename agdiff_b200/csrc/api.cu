@@ -442,26 +442,21 @@ static int adjacency_words(const int32_t* mol_ptr_dev, int n_mols, int* largest_
 }
 
 // Pair map of the local edges (CSC order: grouped by destination, sources ascending): edge (j -> i) with j > i shares the pair of
-// its twin (i -> j) when that exists with the same type; every other edge is the representative of its own pair.
-static int build_local_pairs(BatchDev& v) {
-  v.n_pairs = 0;
-  const size_t L = (size_t)v.n_local, N = (size_t)v.n_atoms;
-  if (L == 0) return AGD_OK;
-  std::vector<int> src(L), dst(L), typ(L), ptr(N + 1);
-  CUDA_TRY(cudaMemcpy(src.data(), v.lc_src, L * 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(dst.data(), v.lc_dst, L * 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(typ.data(), v.lc_type, L * 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(ptr.data(), v.lc_in_ptr, (N + 1) * 4, cudaMemcpyDeviceToHost));
-  std::vector<int> of(L, -1), ps, pd, pt;
+// its twin (i -> j) when that exists with the same type; every other edge is the representative of its own pair.  Host arrays in,
+// host vectors out (no CUDA: also exported as agd_host_local_pairs for the CPU tests).
+static void local_pair_map(const int* src, const int* dst, const int* typ, const int* ptr, size_t L, size_t N, std::vector<int>& of,
+                           std::vector<int>& ps, std::vector<int>& pd, std::vector<int>& pt) {
+  of.assign(L, -1);
+  ps.clear(); pd.clear(); pt.clear();
   ps.reserve(L / 2 + 1); pd.reserve(L / 2 + 1); pt.reserve(L / 2 + 1);
   auto twin = [&](size_t e) -> long {   // the edge dst[e] -> src[e], found in the segment of destination src[e]
     const int j = src[e], i = dst[e];
-    if (j < 0 || (size_t)j >= N) return -1;
-    const int* lo = src.data() + ptr[j];
-    const int* hi = src.data() + ptr[j + 1];
+    if (j < 0 || (size_t)j >= N || ptr[j] < 0 || ptr[j + 1] < ptr[j] || (size_t)ptr[j + 1] > L) return -1;
+    const int* lo = src + ptr[j];
+    const int* hi = src + ptr[j + 1];
     const int* it = std::lower_bound(lo, hi, i);
     if (it == hi || *it != i) return -1;
-    const long t = it - src.data();
+    const long t = it - src;
     return (dst[t] == j && typ[t] == typ[e]) ? t : -1;
   };
   auto open_pair = [&](size_t e) {
@@ -476,6 +471,30 @@ static int build_local_pairs(BatchDev& v) {
     if (t >= 0 && of[t] >= 0 && src[t] < dst[t]) of[e] = of[t];
     else open_pair(e);
   }
+}
+
+int agd_host_local_pairs(const int32_t* src, const int32_t* dst, const int32_t* type, const int32_t* in_ptr, int32_t n_local,
+                         int32_t n_atoms, int32_t* pair_of, int32_t* n_pairs) {
+  if (n_local < 0 || n_atoms < 0 || !n_pairs || (n_local > 0 && (!src || !dst || !type || !in_ptr || !pair_of)))
+    return fail(AGD_ERR_INVALID, "bad arguments");
+  std::vector<int> of, ps, pd, pt;
+  local_pair_map(src, dst, type, in_ptr, (size_t)n_local, (size_t)n_atoms, of, ps, pd, pt);
+  for (int32_t e = 0; e < n_local; ++e) pair_of[e] = of[(size_t)e];
+  *n_pairs = (int32_t)ps.size();
+  return AGD_OK;
+}
+
+static int build_local_pairs(BatchDev& v) {
+  v.n_pairs = 0;
+  const size_t L = (size_t)v.n_local, N = (size_t)v.n_atoms;
+  if (L == 0) return AGD_OK;
+  std::vector<int> src(L), dst(L), typ(L), ptr(N + 1);
+  CUDA_TRY(cudaMemcpy(src.data(), v.lc_src, L * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(dst.data(), v.lc_dst, L * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(typ.data(), v.lc_type, L * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(ptr.data(), v.lc_in_ptr, (N + 1) * 4, cudaMemcpyDeviceToHost));
+  std::vector<int> of, ps, pd, pt;
+  local_pair_map(src.data(), dst.data(), typ.data(), ptr.data(), L, N, of, ps, pd, pt);
   const size_t P = ps.size();
   std::vector<int> ident(P);
   for (size_t p = 0; p < P; ++p) ident[p] = (int)p;

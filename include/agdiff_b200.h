@@ -199,6 +199,11 @@ int agd_op_kabsch_rmsd(const float* ref /*dev [n_ref][n_atoms][3]*/, const float
                        const int32_t* sel /*dev [n_sel] or NULL*/, int32_t n_sel, int32_t n_atoms, int32_t n_ref, int32_t n_gen,
                        float* out /*dev [n_ref][n_gen]*/, void* stream);
 
+/* host-only helper (no CUDA call): the pair map the local branch uses for a CSC-sorted local edge list given as HOST
+ * arrays - pair_of[e] in [0, *n_pairs); two edges share a pair iff they are each other's reverse with the same type. */
+int agd_host_local_pairs(const int32_t* src, const int32_t* dst, const int32_t* type, const int32_t* in_ptr /*host [n_atoms+1]*/,
+                         int32_t n_local, int32_t n_atoms, int32_t* pair_of /*host [n_local]*/, int32_t* n_pairs);
+
 /* debugging / tests: copy an internal per-batch tensor to a caller device buffer.  Names:
  * "g2", "h_global", "h_local", "ea_local", "xcat", "agg", "filt".  Returns element count or <0. */
 int64_t agd_debug_fetch(agd_batch* b, const char* name, float* dst_dev, int64_t capacity);

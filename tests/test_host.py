@@ -343,3 +343,59 @@ def test_evaluation_has_no_cpu_path():
     from agdiff_b200 import evaluation
     with pytest.raises(RuntimeError):
         evaluation.rmsd_matrix(np.zeros((1, 4, 3)), np.zeros((1, 4, 3)), device="cpu")
+
+
+def test_local_pair_map_properties():
+    """agd_host_local_pairs (the host routine behind the pair mode of the local branch, no CUDA involved): on symmetric bond
+    graphs every pair holds exactly the two directions of one bond; with dropped directions, changed types, self loops and an
+    unsorted segment the map stays valid - two edges share a pair only if they are each other's reverse with equal type"""
+    import ctypes as C
+    from agdiff_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+
+    def run(src, dst, typ, n):
+        order = np.lexsort((src, dst))                      # CSC: grouped by destination, sources ascending
+        src, dst, typ = (np.ascontiguousarray(a[order], dtype=np.int32) for a in (src, dst, typ))
+        ptr = np.zeros(n + 1, np.int32)
+        ptr[1:] = np.cumsum(np.bincount(dst, minlength=n))
+        of = np.full(src.size, -7, np.int32)
+        P = C.c_int32(-1)
+        _lib.check(lib.agd_host_local_pairs(src.ctypes.data, dst.ctypes.data, typ.ctypes.data, ptr.ctypes.data, src.size, n,
+                                            of.ctypes.data, C.byref(P)))
+        return src, dst, typ, of, P.value
+
+    def check(src, dst, typ, of, P):
+        assert of.min() >= 0 and of.max() == P - 1 and np.unique(of).size == P
+        members = {}
+        for e, p in enumerate(of):
+            members.setdefault(int(p), []).append(e)
+        have = {(int(s), int(d)): int(t) for s, d, t in zip(src, dst, typ)}
+        for p, es in members.items():
+            assert len(es) <= 2
+            if len(es) == 2:
+                a, b = es
+                assert src[a] == dst[b] and dst[a] == src[b] and typ[a] == typ[b] and src[a] != dst[a]
+        for e in range(src.size):                            # completeness: a same-type twin always shares the pair
+            tw = have.get((int(dst[e]), int(src[e])))
+            if tw is not None and tw == int(typ[e]) and src[e] != dst[e]:
+                assert len(members[int(of[e])]) == 2
+        return members
+
+    for mol in synth.drugs_like(6, seed=5, force_max=False):
+        ext = graph.extend_bond_order_host(mol)
+        src, dst, typ = ext.bond_index[0], ext.bond_index[1], ext.bond_type
+        s, d, t, of, P = run(src, dst, typ, ext.num_nodes)
+        check(s, d, t, of, P)
+        assert P * 2 == s.size                                # symmetric graph: exactly half
+        keep = rng.random(s.size) > 0.2                       # drop directions, flip some types, add self loops
+        t2 = t.copy()
+        t2[rng.random(s.size) < 0.1] += 1
+        s2 = np.concatenate([s[keep], np.array([0, 3], np.int32)])
+        d2 = np.concatenate([d[keep], np.array([0, 3], np.int32)])
+        t3 = np.concatenate([t2[keep], np.array([1, 2], np.int32)])
+        check(*run(s2, d2, t3, ext.num_nodes)[0:3], *run(s2, d2, t3, ext.num_nodes)[3:5])
+    # an empty list is fine
+    P = C.c_int32(-1)
+    _lib.check(lib.agd_host_local_pairs(None, None, None, None, 0, 4, None, C.byref(P)))
+    assert P.value == 0
